@@ -1,0 +1,916 @@
+// C ABI: context management and the analyze path (frames, detector, LK, streaming
+// analyzer).  See include/polychase_b200.h for the reference interfaces each entry point
+// replaces.
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+#include <mutex>
+
+#include "context.h"
+
+namespace pc {
+
+static std::mutex g_err_mtx;
+static std::string g_err;
+
+void set_global_error(const std::string& msg) {
+    std::lock_guard<std::mutex> lk(g_err_mtx);
+    g_err = msg;
+}
+
+int fail(pc_ctx* c, int code, const std::string& msg) {
+    if (c) c->err = msg;
+    else set_global_error(msg);
+    return code;
+}
+
+int cuda_fail(pc_ctx* c, cudaError_t e, const char* what, const char* file, int line) {
+    std::string m = std::string("CUDA error ") + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ") at " + file +
+                    ":" + std::to_string(line) + " in " + what;
+    return fail(c, e == cudaErrorMemoryAllocation ? PC_ERR_NOMEM : PC_ERR_CUDA, m);
+}
+
+static cudaEvent_t get_event(pc_ctx* c) {
+    if (!c->event_pool.empty()) {
+        cudaEvent_t e = c->event_pool.back();
+        c->event_pool.pop_back();
+        return e;
+    }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+}
+
+void span_begin(pc_ctx* c, int family, cudaStream_t s) {
+    if (!c->timing) return;
+    TimedSpan sp;
+    sp.family = family;
+    sp.start = get_event(c);
+    sp.stop = get_event(c);
+    cudaEventRecord(sp.start, s);
+    c->spans.push_back(sp);
+}
+
+void span_end(pc_ctx* c, cudaStream_t s) {
+    if (!c->timing || c->spans.empty()) return;
+    cudaEventRecord(c->spans.back().stop, s);
+}
+
+int check_launch(pc_ctx* c, const char* what, int n_kernels) {
+    c->launches += (uint64_t)n_kernels;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(c, e, what, __FILE__, __LINE__);
+    return PC_OK;
+}
+
+FrameSlot* find_slot(pc_ctx* c, int32_t frame_id) {
+    for (auto& s : c->slots)
+        if (s.used && s.frame_id == frame_id) return &s;
+    return nullptr;
+}
+
+PyramidView view_of(const FrameSlot& f) {
+    PyramidView v{};
+    v.levels = f.levels;
+    for (int i = 0; i < kMaxLevels; i++) {
+        v.data[i] = f.level[i].data;
+        v.w[i] = f.level[i].w;
+        v.h[i] = f.level[i].h;
+        v.pitch[i] = f.level[i].pitch;
+    }
+    return v;
+}
+
+static FrameSlot* acquire_slot(pc_ctx* c, int32_t frame_id) {
+    FrameSlot* s = find_slot(c, frame_id);
+    if (!s) {
+        for (auto& t : c->slots)
+            if (!t.used) { s = &t; break; }
+    }
+    if (!s) {  // evict the least recently uploaded frame
+        s = &c->slots[0];
+        for (auto& t : c->slots)
+            if (t.stamp < s->stamp) s = &t;
+    }
+    s->used = true;
+    s->frame_id = frame_id;
+    s->stamp = ++c->stamp;
+    s->has_kps = false;
+    s->n_kps_host = -1;
+    return s;
+}
+
+// cv::buildOpticalFlowPyramid level rule: after producing level L the next size is
+// ((w+1)/2, (h+1)/2); the pyramid stops at L if that size is <= winSize in either dimension.
+static int plan_levels(FrameSlot* f, int w, int h, int win, int max_level) {
+    int levels = 0;
+    int lw = w, lh = h;
+    for (int L = 0; L <= max_level && L < kMaxLevels; L++) {
+        f->level[L].w = lw;
+        f->level[L].h = lh;
+        levels = L + 1;
+        lw = (lw + 1) / 2;
+        lh = (lh + 1) / 2;
+        if (lw <= win || lh <= win) break;
+    }
+    return levels;
+}
+
+static int validate_flow_opts(pc_ctx* c, const pc_flow_opts* o) {
+    extern bool lk_window_supported(int);
+    PC_CHECK(c, o != nullptr, "flow options are required");
+    PC_CHECK(c, lk_window_supported(o->window_size), "window_size must be in [3,16]");
+    PC_CHECK(c, o->max_level >= 0 && o->max_level < kMaxLevels, "max_level must be in [0,5]");
+    return PC_OK;
+}
+
+static int validate_gftt_opts(pc_ctx* c, const pc_gftt_opts* o) {
+    PC_CHECK(c, o != nullptr, "detector options are required");
+    // gftt.cc:19-20
+    PC_CHECK(c, o->quality_level > 0 && o->min_distance >= 0 && o->max_corners >= 0,
+             "options.quality_level > 0 && options.min_distance >= 0 && options.max_corners >= 0");
+    PC_CHECK(c, o->block_size == 3 && o->gradient_size == 3, "only block_size 3 / gradient_size 3 are built");
+    PC_CHECK(c, !o->use_harris, "use_harris is out of scope (never enabled by the addon)");
+    const int gr = std::max(1, o->grid_rows), gc = std::max(1, o->grid_cols);
+    PC_CHECK(c, gr * gc <= c->cell_cap, "grid_rows*grid_cols too large");
+    return PC_OK;
+}
+
+// Builds gray + pyramid of slot f from an RGB (channels==3) or gray (channels==1) device image.
+static int build_pyramid(pc_ctx* c, FrameSlot* f, const uint8_t* img_dev, size_t stride, int channels, int w, int h,
+                         const pc_flow_opts* fo, cudaStream_t s) {
+    f->w = w;
+    f->h = h;
+    f->levels = plan_levels(f, w, h, fo->window_size, fo->max_level);
+    span_begin(c, KF_GRAY_PYR, s);
+    if (channels == 3) launch_rgb_to_gray(img_dev, stride, f->level[0], s);
+    else launch_copy_gray(img_dev, stride, f->level[0], s);
+    for (int L = 1; L < f->levels; L++) launch_pyr_down(f->level[L - 1], f->level[L], s);
+    span_end(c, s);
+    return check_launch(c, "gray+pyramid", f->levels + (channels == 3 && (w % 16) ? 1 : 0));
+}
+
+static int run_detector(pc_ctx* c, FrameSlot* f, const pc_gftt_opts* go, cudaStream_t s) {
+    DetectGrid g;
+    g.grid_rows = std::max(1, go->grid_rows);
+    g.grid_cols = std::max(1, go->grid_cols);
+    g.block_h = (f->h + g.grid_rows - 1) / g.grid_rows;   // gftt.cc:42-43
+    g.block_w = (f->w + g.grid_cols - 1) / g.grid_cols;
+    span_begin(c, KF_MIN_EIG, s);
+    launch_min_eig(f->level[0], c->eig, c->eig_pitch, g, c->cell_max, s);
+    span_end(c, s);
+    span_begin(c, KF_SELECT, s);
+    launch_nms_candidates(c->eig, c->eig_pitch, f->w, f->h, g, c->cell_max, go->quality_level, c->state,
+                          c->state_pitch, c->cand, c->cand_cap, c->cand_count, s);
+    SelectWorkspace ws = c->sel;
+    ws.accepted_count = f->n_accepted;
+    ws.remaining = f->greedy_remaining;
+    launch_select(c->cand, c->cand_count, c->cand_cap, c->eig, c->eig_pitch, c->state, c->state_pitch, f->w, f->h,
+                  go->min_distance, go->max_corners, ws, f->kps, c->lim.max_features, f->n_kps, c->sm_count, s);
+    span_end(c, s);
+    f->has_kps = true;
+    f->n_kps_host = -1;
+    return check_launch(c, "detector", 6);
+}
+
+static LKParams make_lk_params(const pc_flow_opts* fo) {
+    LKParams p;
+    p.win = fo->window_size;
+    p.max_level = fo->max_level;
+    // cv::calcOpticalFlowPyrLK clamps the criteria: maxCount to [0,100], epsilon to [0,10]
+    p.iters = std::min(std::max(fo->term_max_iters, 0), 100);
+    p.eps = std::min(std::max(fo->term_epsilon, 0.0), 10.0);
+    p.min_eig = fo->min_eigen_threshold;
+    return p;
+}
+
+static void fill_pair(pc_ctx* c, LKPair& p, const FrameSlot& a, const FrameSlot& b, int k, const PairOut& out) {
+    const int cap = c->lim.max_features;
+    p.a = view_of(a);
+    p.b = view_of(b);
+    p.pts = a.kps;
+    p.n_pts = a.n_kps;
+    p.next = c->lk_next + (size_t)k * cap * 2;
+    p.status = c->lk_status + (size_t)k * cap;
+    p.err = c->lk_err + (size_t)k * cap;
+    p.out_idx = out.idx;
+    p.out_tgt = out.tgt;
+    p.out_err = out.err;
+    p.out_count = out.count;
+}
+
+static int alloc_pair_out(pc_ctx* c, PairOut& o, int cap, bool pinned) {
+    if (pinned) {
+        PC_CUDA(c, cudaMallocHost(&o.idx, sizeof(uint32_t) * cap));
+        PC_CUDA(c, cudaMallocHost(&o.tgt, sizeof(float) * 2 * cap));
+        PC_CUDA(c, cudaMallocHost(&o.err, sizeof(float) * cap));
+        PC_CUDA(c, cudaMallocHost(&o.count, sizeof(int)));
+    } else {
+        PC_CUDA(c, cudaMalloc(&o.idx, sizeof(uint32_t) * cap));
+        PC_CUDA(c, cudaMalloc(&o.tgt, sizeof(float) * 2 * cap));
+        PC_CUDA(c, cudaMalloc(&o.err, sizeof(float) * cap));
+        PC_CUDA(c, cudaMalloc(&o.count, sizeof(int)));
+    }
+    return PC_OK;
+}
+
+static void free_pair_out(PairOut& o, bool pinned) {
+    if (pinned) {
+        cudaFreeHost(o.idx); cudaFreeHost(o.tgt); cudaFreeHost(o.err); cudaFreeHost(o.count);
+    } else {
+        cudaFree(o.idx); cudaFree(o.tgt); cudaFree(o.err); cudaFree(o.count);
+    }
+    o = PairOut{};
+}
+
+}  // namespace pc
+
+using namespace pc;
+
+pc_ctx::~pc_ctx() {
+    cudaSetDevice(device);
+    if (compute) cudaStreamSynchronize(compute);
+    if (h2d) cudaStreamSynchronize(h2d);
+    if (d2h) cudaStreamSynchronize(d2h);
+    for (auto& s : slots) {
+        if (s.level[0].data) cudaFree(s.level[0].data);
+        cudaFree(s.kps); cudaFree(s.n_kps);
+    }
+    cudaFree(eig); cudaFree(state); cudaFree(cell_max); cudaFree(cand); cudaFree(cand_count);
+    cudaFree(sel.accepted); cudaFree(sel.sorted); cudaFree(sel.round_counters); cudaFree(sel.cub_temp);
+    cudaFree(lk_next); cudaFree(lk_status); cudaFree(lk_err);
+    free_pair_out(sync_out, false);
+    cudaFree(rgb_scratch);
+    for (auto& st : stages) {
+        cudaFree(st.rgb_dev);
+        for (int k = 0; k < 8; k++) { free_pair_out(st.dev[k], false); free_pair_out(st.host[k], true); }
+        cudaFreeHost(st.kps_host); cudaFreeHost(st.counts_host);
+        if (st.uploaded) cudaEventDestroy(st.uploaded);
+        if (st.gray_done) cudaEventDestroy(st.gray_done);
+        if (st.computed) cudaEventDestroy(st.computed);
+        if (st.downloaded) cudaEventDestroy(st.downloaded);
+    }
+    cudaFree(tex);
+    for (auto& sp : spans) { cudaEventDestroy(sp.start); cudaEventDestroy(sp.stop); }
+    for (auto e : event_pool) cudaEventDestroy(e);
+    if (mesh) free_mesh(mesh);
+    if (ba) free_ba(ba);
+    if (compute) cudaStreamDestroy(compute);
+    if (h2d) cudaStreamDestroy(h2d);
+    if (d2h) cudaStreamDestroy(d2h);
+}
+
+extern "C" {
+
+void pc_default_gftt_opts(pc_gftt_opts* o) {
+    o->quality_level = 0.01; o->min_distance = 5.0; o->block_size = 3; o->gradient_size = 3; o->max_corners = 0;
+    o->use_harris = 0; o->harris_k = 0.04; o->grid_rows = 4; o->grid_cols = 4;
+}
+void pc_default_flow_opts(pc_flow_opts* o) {
+    o->window_size = 10; o->max_level = 3; o->term_max_iters = 30; o->term_epsilon = 0.01;
+    o->min_eigen_threshold = 1e-4;
+}
+void pc_default_bundle_opts(pc_bundle_opts* o) {
+    o->max_iterations = 100; o->max_allowed_parallelism = 8; o->loss_type = 1; o->loss_scale = 1.0f;
+    o->gradient_tol = 1e-10f; o->step_tol = 1e-8f; o->initial_lambda = 1e-5f; o->min_lambda = 1e-10f;
+    o->max_lambda = 1e10f; o->verbose = 0;
+}
+const char* pc_version(void) { return "polychase_b200 0.1.0 (sm_100a)"; }
+
+const char* pc_last_error(pc_ctx* c) {
+    if (c) return c->err.c_str();
+    static thread_local std::string copy;
+    std::lock_guard<std::mutex> lk(g_err_mtx);
+    copy = g_err;
+    return copy.c_str();
+}
+
+int pc_create(const pc_limits* limits, pc_ctx** out) {
+    if (!out) return fail(nullptr, PC_ERR_INVALID, "pc_create: out is NULL");
+    *out = nullptr;
+    pc_limits lim{};
+    if (limits) lim = *limits;
+    if (lim.max_width <= 0) lim.max_width = 3840;
+    if (lim.max_height <= 0) lim.max_height = 2160;
+    if (lim.max_features <= 0) lim.max_features = 16384;
+    if (lim.ring_frames <= 0) lim.ring_frames = 20;
+    if (lim.pipeline_depth <= 0) lim.pipeline_depth = 4;
+    if (lim.ring_frames < 9 + lim.pipeline_depth) lim.ring_frames = 9 + lim.pipeline_depth;
+
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, PC_ERR_CUDA,
+                    std::string("pc_create: no CUDA device available (") + cudaGetErrorString(e) +
+                        "); this library has no CPU fallback");
+    if (lim.device < 0 || lim.device >= ndev) return fail(nullptr, PC_ERR_INVALID, "pc_create: bad device ordinal");
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, lim.device);
+    if (prop.major != 10)
+        return fail(nullptr, PC_ERR_CUDA,
+                    std::string("pc_create: device '") + prop.name + "' is sm_" + std::to_string(prop.major) +
+                        std::to_string(prop.minor) + "; this library is built for sm_100a only");
+    std::unique_ptr<pc_ctx> c(new pc_ctx());
+    c->lim = lim;
+    c->device = lim.device;
+    c->sm_count = prop.multiProcessorCount;
+    pc_ctx* cp = c.get();
+    PC_CUDA(nullptr, cudaSetDevice(lim.device));
+    PC_CUDA(nullptr, cudaStreamCreateWithFlags(&cp->compute, cudaStreamNonBlocking));
+    PC_CUDA(nullptr, cudaStreamCreateWithFlags(&cp->h2d, cudaStreamNonBlocking));
+    PC_CUDA(nullptr, cudaStreamCreateWithFlags(&cp->d2h, cudaStreamNonBlocking));
+
+    const int W = lim.max_width, H = lim.max_height, cap = lim.max_features;
+    // frame ring: all levels of a slot in one allocation
+    cp->slots.resize(lim.ring_frames);
+    for (auto& s : cp->slots) {
+        size_t total = 0;
+        int lw = W, lh = H;
+        size_t offs[kMaxLevels];
+        int pitches[kMaxLevels];
+        for (int L = 0; L < kMaxLevels; L++) {
+            pitches[L] = (lw + 127) / 128 * 128;
+            offs[L] = total;
+            total += (size_t)pitches[L] * lh;
+            total = (total + 255) / 256 * 256;
+            lw = (lw + 1) / 2; lh = (lh + 1) / 2;
+        }
+        uint8_t* base = nullptr;
+        PC_CUDA(nullptr, cudaMalloc(&base, total));
+        for (int L = 0; L < kMaxLevels; L++) { s.level[L].data = base + offs[L]; s.level[L].pitch = pitches[L]; }
+        PC_CUDA(nullptr, cudaMalloc(&s.kps, sizeof(float) * 2 * cap));
+        PC_CUDA(nullptr, cudaMalloc(&s.n_kps, sizeof(int) * 4));
+        PC_CUDA(nullptr, cudaMemset(s.n_kps, 0, sizeof(int) * 4));
+        s.n_accepted = s.n_kps + 1;
+        s.greedy_remaining = s.n_kps + 2;
+    }
+    cp->eig_pitch = (W + 31) / 32 * 32;
+    PC_CUDA(nullptr, cudaMalloc(&cp->eig, sizeof(float) * (size_t)cp->eig_pitch * H));
+    cp->state_pitch = (W + 127) / 128 * 128;
+    PC_CUDA(nullptr, cudaMalloc(&cp->state, (size_t)cp->state_pitch * H));
+    cp->cell_cap = 4096;
+    PC_CUDA(nullptr, cudaMalloc(&cp->cell_max, sizeof(int) * cp->cell_cap));
+    // 3x3 NMS leaves at most one candidate per 2x2 block except on plateaus; w*h/4 is ample
+    cp->cand_cap = std::max(1024, (int)(((size_t)W * H) / 4));
+    PC_CUDA(nullptr, cudaMalloc(&cp->cand, sizeof(unsigned long long) * cp->cand_cap));
+    PC_CUDA(nullptr, cudaMalloc(&cp->cand_count, sizeof(int)));
+    cp->sel.cap = cp->cand_cap;
+    PC_CUDA(nullptr, cudaMalloc(&cp->sel.accepted, sizeof(unsigned long long) * cp->cand_cap));
+    PC_CUDA(nullptr, cudaMalloc(&cp->sel.sorted, sizeof(unsigned long long) * cp->cand_cap));
+    PC_CUDA(nullptr, cudaMalloc(&cp->sel.round_counters, sizeof(int) * kMaxGreedyRounds));
+    cp->sel.cub_temp_bytes = select_cub_temp_bytes(cp->cand_cap);
+    PC_CUDA(nullptr, cudaMalloc(&cp->sel.cub_temp, cp->sel.cub_temp_bytes));
+    PC_CUDA(nullptr, cudaMalloc(&cp->lk_next, sizeof(float) * 2 * (size_t)cap * 8));
+    PC_CUDA(nullptr, cudaMalloc(&cp->lk_status, (size_t)cap * 8));
+    PC_CUDA(nullptr, cudaMalloc(&cp->lk_err, sizeof(float) * (size_t)cap * 8));
+    int rc = alloc_pair_out(nullptr, cp->sync_out, cap, false);
+    if (rc) return rc;
+    *out = c.release();
+    return PC_OK;
+}
+
+void pc_destroy(pc_ctx* c) { delete c; }
+
+int pc_synchronize(pc_ctx* c) {
+    PC_CUDA(c, cudaSetDevice(c->device));
+    PC_CUDA(c, cudaStreamSynchronize(c->h2d));
+    PC_CUDA(c, cudaStreamSynchronize(c->compute));
+    PC_CUDA(c, cudaStreamSynchronize(c->d2h));
+    return PC_OK;
+}
+
+uint64_t pc_kernel_launches(pc_ctx* c) { return c->launches; }
+
+// ---- frames ---------------------------------------------------------------------------
+static int frame_common(pc_ctx* c, int32_t frame_id, const uint8_t* img, int w, int h, size_t stride, int channels,
+                        bool on_device, const pc_flow_opts* fo) {
+    PC_CUDA(c, cudaSetDevice(c->device));
+    int rc = validate_flow_opts(c, fo);
+    if (rc) return rc;
+    PC_CHECK(c, img != nullptr, "image pointer is NULL");
+    PC_CHECK(c, w >= 16 && h >= 16, "frames smaller than 16x16 are not supported");
+    PC_CHECK(c, w <= c->lim.max_width && h <= c->lim.max_height, "frame larger than the context limits");
+    PC_CHECK(c, stride >= (size_t)w * channels, "stride smaller than a row");
+    FrameSlot* f = acquire_slot(c, frame_id);
+    const uint8_t* dev = img;
+    if (!on_device) {
+        const size_t bytes = stride * (size_t)h;
+        if (c->rgb_scratch_bytes < bytes) {
+            cudaFree(c->rgb_scratch);
+            c->rgb_scratch = nullptr;
+            c->rgb_scratch_bytes = 0;
+            PC_CUDA(c, cudaMalloc(&c->rgb_scratch, bytes));
+            c->rgb_scratch_bytes = bytes;
+        }
+        PC_CUDA(c, cudaMemcpyAsync(c->rgb_scratch, img, bytes, cudaMemcpyHostToDevice, c->compute));
+        dev = c->rgb_scratch;
+    }
+    rc = build_pyramid(c, f, dev, stride, channels, w, h, fo, c->compute);
+    if (rc) return rc;
+    PC_CUDA(c, cudaStreamSynchronize(c->compute));
+    return PC_OK;
+}
+
+int pc_frame_upload_rgb8(pc_ctx* c, int32_t frame_id, const uint8_t* rgb, int w, int h, size_t stride,
+                         const pc_flow_opts* fo) {
+    return frame_common(c, frame_id, rgb, w, h, stride, 3, false, fo);
+}
+int pc_frame_from_device_rgb8(pc_ctx* c, int32_t frame_id, const uint8_t* rgb, int w, int h, size_t stride,
+                              const pc_flow_opts* fo) {
+    return frame_common(c, frame_id, rgb, w, h, stride, 3, true, fo);
+}
+int pc_frame_upload_gray8(pc_ctx* c, int32_t frame_id, const uint8_t* gray, int w, int h, size_t stride,
+                          const pc_flow_opts* fo) {
+    return frame_common(c, frame_id, gray, w, h, stride, 1, false, fo);
+}
+
+int pc_frame_release(pc_ctx* c, int32_t frame_id) {
+    FrameSlot* f = find_slot(c, frame_id);
+    if (!f) return fail(c, PC_ERR_NOT_FOUND, "frame " + std::to_string(frame_id) + " is not resident");
+    f->used = false;
+    return PC_OK;
+}
+
+int pc_frame_num_levels(pc_ctx* c, int32_t frame_id, int* levels_out) {
+    FrameSlot* f = find_slot(c, frame_id);
+    if (!f) return fail(c, PC_ERR_NOT_FOUND, "frame " + std::to_string(frame_id) + " is not resident");
+    *levels_out = f->levels;
+    return PC_OK;
+}
+
+int pc_frame_read_level(pc_ctx* c, int32_t frame_id, int level, uint8_t* out, size_t cap, int* w_out, int* h_out) {
+    PC_CUDA(c, cudaSetDevice(c->device));
+    FrameSlot* f = find_slot(c, frame_id);
+    if (!f) return fail(c, PC_ERR_NOT_FOUND, "frame " + std::to_string(frame_id) + " is not resident");
+    PC_CHECK(c, level >= 0 && level < f->levels, "no such pyramid level");
+    const Image8& im = f->level[level];
+    if (w_out) *w_out = im.w;
+    if (h_out) *h_out = im.h;
+    if (!out) return PC_OK;
+    if (cap < (size_t)im.w * im.h) return fail(c, PC_ERR_CAPACITY, "output buffer too small for level");
+    PC_CUDA(c, cudaMemcpy2DAsync(out, im.w, im.data, im.pitch, im.w, im.h, cudaMemcpyDeviceToHost, c->compute));
+    PC_CUDA(c, cudaStreamSynchronize(c->compute));
+    return PC_OK;
+}
+
+// ---- detector -------------------------------------------------------------------------
+static int fetch_kps_count(pc_ctx* c, FrameSlot* f) {
+    int host[3];
+    PC_CUDA(c, cudaMemcpyAsync(host, f->n_kps, sizeof(int) * 3, cudaMemcpyDeviceToHost, c->compute));
+    PC_CUDA(c, cudaStreamSynchronize(c->compute));
+    f->n_kps_host = host[0];
+    return PC_OK;
+}
+
+static int check_detector_result(pc_ctx* c, const pc_gftt_opts* go, int n_kps, int n_accepted, int remaining,
+                                 int cand_count) {
+    if (remaining != 0)
+        return fail(c, PC_ERR_STATE, "min-distance suppression did not reach its fixed point in " +
+                                         std::to_string(kMaxGreedyRounds) + " rounds");
+    if (cand_count > c->cand_cap) return fail(c, PC_ERR_CAPACITY, "corner candidate buffer overflow");
+    const int want = go->max_corners > 0 ? std::min(go->max_corners, n_accepted) : n_accepted;
+    if (want > c->lim.max_features)
+        return fail(c, PC_ERR_CAPACITY, "detector produced " + std::to_string(want) +
+                                            " corners, above the context's max_features " +
+                                            std::to_string(c->lim.max_features));
+    (void)n_kps;
+    return PC_OK;
+}
+
+int pc_detect(pc_ctx* c, int32_t frame_id, const pc_gftt_opts* go, float* kps_out, int cap, int* n_out) {
+    PC_CUDA(c, cudaSetDevice(c->device));
+    int rc = validate_gftt_opts(c, go);
+    if (rc) return rc;
+    FrameSlot* f = find_slot(c, frame_id);
+    if (!f) return fail(c, PC_ERR_NOT_FOUND, "frame " + std::to_string(frame_id) + " is not resident");
+    rc = run_detector(c, f, go, c->compute);
+    if (rc) return rc;
+    int host[3], ncand = 0;
+    PC_CUDA(c, cudaMemcpyAsync(host, f->n_kps, sizeof(int) * 3, cudaMemcpyDeviceToHost, c->compute));
+    PC_CUDA(c, cudaMemcpyAsync(&ncand, c->cand_count, sizeof(int), cudaMemcpyDeviceToHost, c->compute));
+    PC_CUDA(c, cudaStreamSynchronize(c->compute));
+    rc = check_detector_result(c, go, host[0], host[1], host[2], ncand);
+    if (rc) return rc;
+    f->n_kps_host = host[0];
+    if (n_out) *n_out = host[0];
+    if (kps_out) {
+        if (cap < host[0]) return fail(c, PC_ERR_CAPACITY, "keypoint output buffer too small");
+        PC_CUDA(c, cudaMemcpy(kps_out, f->kps, sizeof(float) * 2 * host[0], cudaMemcpyDeviceToHost));
+    }
+    return PC_OK;
+}
+
+int pc_min_eig_map(pc_ctx* c, int32_t frame_id, float* eig_out, size_t cap_floats) {
+    PC_CUDA(c, cudaSetDevice(c->device));
+    FrameSlot* f = find_slot(c, frame_id);
+    if (!f) return fail(c, PC_ERR_NOT_FOUND, "frame " + std::to_string(frame_id) + " is not resident");
+    if (cap_floats < (size_t)f->w * f->h) return fail(c, PC_ERR_CAPACITY, "eig output buffer too small");
+    DetectGrid g{1, 1, f->w, f->h};
+    span_begin(c, KF_MIN_EIG, c->compute);
+    launch_min_eig(f->level[0], c->eig, c->eig_pitch, g, c->cell_max, c->compute);
+    span_end(c, c->compute);
+    int rc = check_launch(c, "min_eig", 2);
+    if (rc) return rc;
+    PC_CUDA(c, cudaMemcpy2DAsync(eig_out, sizeof(float) * f->w, c->eig, sizeof(float) * c->eig_pitch,
+                                 sizeof(float) * f->w, f->h, cudaMemcpyDeviceToHost, c->compute));
+    PC_CUDA(c, cudaStreamSynchronize(c->compute));
+    return PC_OK;
+}
+
+int pc_set_keypoints(pc_ctx* c, int32_t frame_id, const float* kps, int n) {
+    PC_CUDA(c, cudaSetDevice(c->device));
+    FrameSlot* f = find_slot(c, frame_id);
+    if (!f) return fail(c, PC_ERR_NOT_FOUND, "frame " + std::to_string(frame_id) + " is not resident");
+    PC_CHECK(c, n >= 0 && (n == 0 || kps != nullptr), "bad keypoint array");
+    if (n > c->lim.max_features) return fail(c, PC_ERR_CAPACITY, "more keypoints than the context's max_features");
+    int hdr[3] = {n, n, 0};
+    PC_CUDA(c, cudaMemcpyAsync(f->kps, kps, sizeof(float) * 2 * n, cudaMemcpyHostToDevice, c->compute));
+    PC_CUDA(c, cudaMemcpyAsync(f->n_kps, hdr, sizeof(hdr), cudaMemcpyHostToDevice, c->compute));
+    PC_CUDA(c, cudaStreamSynchronize(c->compute));
+    f->has_kps = true;
+    f->n_kps_host = n;
+    return PC_OK;
+}
+
+// ---- LK ---------------------------------------------------------------------------------
+static int lk_sync_common(pc_ctx* c, int32_t from, int32_t to, const pc_flow_opts* fo, FrameSlot** fa_out) {
+    PC_CUDA(c, cudaSetDevice(c->device));
+    int rc = validate_flow_opts(c, fo);
+    if (rc) return rc;
+    FrameSlot* a = find_slot(c, from);
+    FrameSlot* b = find_slot(c, to);
+    if (!a) return fail(c, PC_ERR_NOT_FOUND, "frame " + std::to_string(from) + " is not resident");
+    if (!b) return fail(c, PC_ERR_NOT_FOUND, "frame " + std::to_string(to) + " is not resident");
+    if (!a->has_kps) return fail(c, PC_ERR_STATE, "frame " + std::to_string(from) + " has no keypoints");
+    PC_CHECK(c, a->w == b->w && a->h == b->h, "frame sizes differ");
+    if (a->n_kps_host < 0) {
+        rc = fetch_kps_count(c, a);
+        if (rc) return rc;
+    }
+    LKBatch batch{};
+    batch.num_pairs = 1;
+    batch.cap = std::max(1, a->n_kps_host);
+    fill_pair(c, batch.pair[0], *a, *b, 0, c->sync_out);
+    const LKParams p = make_lk_params(fo);
+    if (a->n_kps_host > 0) {
+        span_begin(c, KF_LK, c->compute);
+        launch_lk(batch, p, c->compute);
+        span_end(c, c->compute);
+    }
+    span_begin(c, KF_COMPACT, c->compute);
+    launch_lk_compact(batch, c->compute);
+    span_end(c, c->compute);
+    rc = check_launch(c, "lk", a->n_kps_host > 0 ? 2 : 1);
+    if (rc) return rc;
+    *fa_out = a;
+    return PC_OK;
+}
+
+int pc_lk_pair(pc_ctx* c, int32_t from, int32_t to, const pc_flow_opts* fo, uint32_t* src_idx_out, float* tgt_out,
+               float* err_out, int cap, int* n_out) {
+    FrameSlot* a = nullptr;
+    int rc = lk_sync_common(c, from, to, fo, &a);
+    if (rc) return rc;
+    int n = 0;
+    PC_CUDA(c, cudaMemcpyAsync(&n, c->sync_out.count, sizeof(int), cudaMemcpyDeviceToHost, c->compute));
+    PC_CUDA(c, cudaStreamSynchronize(c->compute));
+    if (n_out) *n_out = n;
+    if (n > cap) return fail(c, PC_ERR_CAPACITY, "flow output buffers too small");
+    if (src_idx_out) PC_CUDA(c, cudaMemcpy(src_idx_out, c->sync_out.idx, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost));
+    if (tgt_out) PC_CUDA(c, cudaMemcpy(tgt_out, c->sync_out.tgt, sizeof(float) * 2 * n, cudaMemcpyDeviceToHost));
+    if (err_out) PC_CUDA(c, cudaMemcpy(err_out, c->sync_out.err, sizeof(float) * n, cudaMemcpyDeviceToHost));
+    return PC_OK;
+}
+
+int pc_lk_raw(pc_ctx* c, int32_t from, int32_t to, const pc_flow_opts* fo, float* next_out, uint8_t* status_out,
+              float* err_out, int cap, int* n_out) {
+    FrameSlot* a = nullptr;
+    int rc = lk_sync_common(c, from, to, fo, &a);
+    if (rc) return rc;
+    PC_CUDA(c, cudaStreamSynchronize(c->compute));
+    const int n = a->n_kps_host;
+    if (n_out) *n_out = n;
+    if (n > cap) return fail(c, PC_ERR_CAPACITY, "flow output buffers too small");
+    if (next_out) PC_CUDA(c, cudaMemcpy(next_out, c->lk_next, sizeof(float) * 2 * n, cudaMemcpyDeviceToHost));
+    if (status_out) PC_CUDA(c, cudaMemcpy(status_out, c->lk_status, (size_t)n, cudaMemcpyDeviceToHost));
+    if (err_out) PC_CUDA(c, cudaMemcpy(err_out, c->lk_err, sizeof(float) * n, cudaMemcpyDeviceToHost));
+    return PC_OK;
+}
+
+// ---- streaming analyzer ----------------------------------------------------------------
+int pc_analyze_begin(pc_ctx* c, const pc_video_info* vi, const pc_gftt_opts* go, const pc_flow_opts* fo) {
+    PC_CUDA(c, cudaSetDevice(c->device));
+    PC_CHECK(c, vi != nullptr, "video info is required");
+    if (c->analyzing) return fail(c, PC_ERR_STATE, "an analyze pass is already open");
+    int rc = validate_gftt_opts(c, go);
+    if (rc) return rc;
+    rc = validate_flow_opts(c, fo);
+    if (rc) return rc;
+    PC_CHECK(c, (int)vi->width <= c->lim.max_width && (int)vi->height <= c->lim.max_height,
+             "video larger than the context limits");
+    PC_CHECK(c, vi->width >= 16 && vi->height >= 16, "frames smaller than 16x16 are not supported");
+    c->vinfo = *vi;
+    c->gopts = *go;
+    c->fopts = *fo;
+    const int cap = c->lim.max_features;
+    if (c->stages.empty()) {
+        c->stages.resize(c->lim.pipeline_depth);
+        for (auto& st : c->stages) {
+            for (int k = 0; k < 8; k++) {
+                rc = alloc_pair_out(c, st.dev[k], cap, false);
+                if (rc) return rc;
+                rc = alloc_pair_out(c, st.host[k], cap, true);
+                if (rc) return rc;
+            }
+            PC_CUDA(c, cudaMallocHost(&st.kps_host, sizeof(float) * 2 * cap));
+            PC_CUDA(c, cudaMallocHost(&st.counts_host, sizeof(int) * 4));
+            PC_CUDA(c, cudaEventCreateWithFlags(&st.uploaded, cudaEventDisableTiming));
+            PC_CUDA(c, cudaEventCreateWithFlags(&st.gray_done, cudaEventDisableTiming));
+            PC_CUDA(c, cudaEventCreateWithFlags(&st.computed, cudaEventDisableTiming));
+            PC_CUDA(c, cudaEventCreateWithFlags(&st.downloaded, cudaEventDisableTiming));
+        }
+    }
+    for (auto& s : c->slots) s.used = false;
+    c->inflight.clear();
+    c->next_stage = 0;
+    c->any_pushed = false;
+    c->preset_kps.clear();
+    for (auto& st : c->stages) { st.busy = false; st.gray_pending = false; }
+    c->analyzing = true;
+    return PC_OK;
+}
+
+int pc_analyze_preset_keypoints(pc_ctx* c, int32_t frame_id, const float* kps, int n) {
+    if (!c->analyzing) return fail(c, PC_ERR_STATE, "no analyze pass is open");
+    PC_CHECK(c, n >= 0 && (n == 0 || kps != nullptr), "bad keypoint array");
+    if (n > c->lim.max_features) return fail(c, PC_ERR_CAPACITY, "more keypoints than the context's max_features");
+    c->preset_kps[frame_id].assign(kps, kps + 2 * (size_t)n);
+    return PC_OK;
+}
+
+int pc_analyze_pending(pc_ctx* c) { return (int)c->inflight.size(); }
+
+int pc_analyze_push_frame(pc_ctx* c, int32_t frame_id, const uint8_t* rgb, size_t stride, int mem_kind) {
+    PC_CUDA(c, cudaSetDevice(c->device));
+    if (!c->analyzing) return fail(c, PC_ERR_STATE, "no analyze pass is open");
+    PC_CHECK(c, rgb != nullptr, "frame pointer is NULL");
+    const int w = (int)c->vinfo.width, h = (int)c->vinfo.height;
+    const int32_t first = c->vinfo.first_frame, last = first + (int32_t)c->vinfo.num_frames;  // opticalflow.cc:220-221
+    PC_CHECK(c, frame_id >= first && frame_id < last, "frame id outside the video range");
+    PC_CHECK(c, !c->any_pushed || frame_id == c->last_pushed + 1, "frames must be pushed in ascending order");
+    PC_CHECK(c, stride >= (size_t)w * 3, "stride smaller than a row");
+    if ((int)c->inflight.size() >= (int)c->stages.size())
+        return fail(c, PC_ERR_STATE, "pipeline full: pop a result before pushing another frame");
+    const int si = c->next_stage;
+    Stage& st = c->stages[si];
+    st.frame_id = frame_id;
+    st.num_pairs = 0;
+
+    FrameSlot* f = acquire_slot(c, frame_id);
+    const uint8_t* dev = rgb;
+    if (mem_kind != PC_MEM_DEVICE) {
+        const size_t bytes = stride * (size_t)h;
+        if (st.rgb_bytes < bytes) {
+            cudaFree(st.rgb_dev);
+            st.rgb_dev = nullptr;
+            st.rgb_bytes = 0;
+            PC_CUDA(c, cudaMalloc(&st.rgb_dev, bytes));
+            st.rgb_bytes = bytes;
+        }
+        // the staging buffer's previous contents must have been consumed by its gray kernel
+        if (st.gray_pending) PC_CUDA(c, cudaStreamWaitEvent(c->h2d, st.gray_done, 0));
+        PC_CUDA(c, cudaMemcpyAsync(st.rgb_dev, rgb, bytes, cudaMemcpyHostToDevice, c->h2d));
+        PC_CUDA(c, cudaEventRecord(st.uploaded, c->h2d));
+        PC_CUDA(c, cudaStreamWaitEvent(c->compute, st.uploaded, 0));
+        dev = st.rgb_dev;
+    }
+    int rc = build_pyramid(c, f, dev, stride, 3, w, h, &c->fopts, c->compute);
+    if (rc) return rc;
+    if (mem_kind != PC_MEM_DEVICE) {
+        PC_CUDA(c, cudaEventRecord(st.gray_done, c->compute));
+        st.gray_pending = true;
+    }
+    auto preset = c->preset_kps.find(frame_id);
+    if (preset != c->preset_kps.end() && !preset->second.empty()) {   // ReadOrGenerateKeypoints
+        const int n = (int)(preset->second.size() / 2);
+        int hdr[3] = {n, n, 0};
+        memcpy(st.kps_host, preset->second.data(), sizeof(float) * 2 * n);
+        memcpy(st.counts_host, hdr, sizeof(hdr));
+        PC_CUDA(c, cudaMemcpyAsync(f->kps, st.kps_host, sizeof(float) * 2 * n, cudaMemcpyHostToDevice, c->compute));
+        PC_CUDA(c, cudaMemcpyAsync(f->n_kps, st.counts_host, sizeof(hdr), cudaMemcpyHostToDevice, c->compute));
+        f->has_kps = true;
+        f->n_kps_host = n;
+        c->preset_kps.erase(preset);
+    } else {
+        rc = run_detector(c, f, &c->gopts, c->compute);
+        if (rc) return rc;
+    }
+    // every pair whose later frame is this one: (j-d -> j) and (j -> j-d), d in {1,2,4,8}
+    LKBatch batch{};
+    batch.cap = c->lim.max_features;
+    if (c->gopts.max_corners > 0) batch.cap = std::min(batch.cap, c->gopts.max_corners);
+    static const int kSkips[4] = {1, 2, 4, 8};   // |image_skips|, opticalflow.cc:76-77
+    int np = 0;
+    for (int k = 0; k < 4; k++) {
+        const int32_t other = frame_id - kSkips[k];
+        if (other < first) continue;
+        FrameSlot* o = find_slot(c, other);
+        if (!o) return fail(c, PC_ERR_STATE, "frame " + std::to_string(other) + " fell out of the ring");
+        st.from[np] = other; st.to[np] = frame_id;
+        fill_pair(c, batch.pair[np], *o, *f, np, st.dev[np]);
+        np++;
+        st.from[np] = frame_id; st.to[np] = other;
+        fill_pair(c, batch.pair[np], *f, *o, np, st.dev[np]);
+        np++;
+    }
+    // presets may exceed max_corners
+    for (int k = 0; k < np; k++) {
+        const FrameSlot* src = find_slot(c, st.from[k]);
+        if (src->n_kps_host > batch.cap) batch.cap = src->n_kps_host;
+    }
+    batch.num_pairs = np;
+    st.num_pairs = np;
+    if (np > 0) {
+        const LKParams p = make_lk_params(&c->fopts);
+        span_begin(c, KF_LK, c->compute);
+        launch_lk(batch, p, c->compute);
+        span_end(c, c->compute);
+        span_begin(c, KF_COMPACT, c->compute);
+        launch_lk_compact(batch, c->compute);
+        span_end(c, c->compute);
+        rc = check_launch(c, "lk batch", 2);
+        if (rc) return rc;
+    }
+    PC_CUDA(c, cudaEventRecord(st.computed, c->compute));
+    // results -> pinned host, on the download stream
+    PC_CUDA(c, cudaStreamWaitEvent(c->d2h, st.computed, 0));
+    PC_CUDA(c, cudaMemcpyAsync(st.counts_host, f->n_kps, sizeof(int) * 3, cudaMemcpyDeviceToHost, c->d2h));
+    for (int k = 0; k < np; k++)
+        PC_CUDA(c, cudaMemcpyAsync(st.host[k].count, st.dev[k].count, sizeof(int), cudaMemcpyDeviceToHost, c->d2h));
+    PC_CUDA(c, cudaEventRecord(st.downloaded, c->d2h));
+    st.busy = true;
+    c->inflight.push_back(si);
+    c->next_stage = (si + 1) % (int)c->stages.size();
+    c->last_pushed = frame_id;
+    c->any_pushed = true;
+    return PC_OK;
+}
+
+int pc_analyze_pop(pc_ctx* c, pc_frame_result* out, int download) {
+    PC_CUDA(c, cudaSetDevice(c->device));
+    if (!c->analyzing) return fail(c, PC_ERR_STATE, "no analyze pass is open");
+    if (c->inflight.empty()) return fail(c, PC_ERR_NOT_FOUND, "no frame is pending");
+    PC_CHECK(c, out != nullptr, "result pointer is NULL");
+    const int si = c->inflight.front();
+    Stage& st = c->stages[si];
+    PC_CUDA(c, cudaEventSynchronize(st.downloaded));
+    memset(out, 0, sizeof(*out));
+    out->frame_id = st.frame_id;
+    const int n_kps = st.counts_host[0];
+    int rc = check_detector_result(c, &c->gopts, n_kps, st.counts_host[1], st.counts_host[2], 0);
+    if (rc) { c->inflight.pop_front(); st.busy = false; return rc; }
+    out->num_keypoints = n_kps;
+    out->num_pairs = st.num_pairs;
+    FrameSlot* f = find_slot(c, st.frame_id);
+    if (f) f->n_kps_host = n_kps;
+    if (download) {
+        // second, size-exact download (counts are known now)
+        if (f && n_kps > 0)
+            PC_CUDA(c, cudaMemcpyAsync(st.kps_host, f->kps, sizeof(float) * 2 * n_kps, cudaMemcpyDeviceToHost, c->d2h));
+        for (int k = 0; k < st.num_pairs; k++) {
+            const int n = *st.host[k].count;
+            if (n <= 0) continue;
+            PC_CUDA(c, cudaMemcpyAsync(st.host[k].idx, st.dev[k].idx, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, c->d2h));
+            PC_CUDA(c, cudaMemcpyAsync(st.host[k].tgt, st.dev[k].tgt, sizeof(float) * 2 * n, cudaMemcpyDeviceToHost, c->d2h));
+            PC_CUDA(c, cudaMemcpyAsync(st.host[k].err, st.dev[k].err, sizeof(float) * n, cudaMemcpyDeviceToHost, c->d2h));
+        }
+        PC_CUDA(c, cudaStreamSynchronize(c->d2h));
+        out->keypoints = st.kps_host;
+    }
+    for (int k = 0; k < st.num_pairs; k++) {
+        pc_pair_rows& r = out->pairs[k];
+        r.image_id_from = st.from[k];
+        r.image_id_to = st.to[k];
+        r.rows = *st.host[k].count;
+        if (download) {
+            r.src_kps_indices = st.host[k].idx;
+            r.tgt_kps = st.host[k].tgt;
+            r.flow_errors = st.host[k].err;
+        }
+    }
+    c->inflight.pop_front();
+    st.busy = false;
+    return PC_OK;
+}
+
+int pc_analyze_end(pc_ctx* c) {
+    if (!c->analyzing) return fail(c, PC_ERR_STATE, "no analyze pass is open");
+    int rc = pc_synchronize(c);
+    c->inflight.clear();
+    for (auto& st : c->stages) st.busy = false;
+    c->analyzing = false;
+    return rc;
+}
+
+// ---- synth / memory helpers --------------------------------------------------------------
+int pc_synth_set_texture(pc_ctx* c, const uint8_t* tex, int w, int h) {
+    PC_CUDA(c, cudaSetDevice(c->device));
+    PC_CHECK(c, tex && w > 0 && h > 0, "bad texture");
+    cudaFree(c->tex);
+    c->tex = nullptr;
+    c->tex_pitch = (w + 127) / 128 * 128;
+    PC_CUDA(c, cudaMalloc(&c->tex, (size_t)c->tex_pitch * h));
+    PC_CUDA(c, cudaMemcpy2D(c->tex, c->tex_pitch, tex, w, w, h, cudaMemcpyHostToDevice));
+    c->tex_w = w;
+    c->tex_h = h;
+    return PC_OK;
+}
+
+static bool invert3x3(const double m[9], double o[9]) {
+    const double a = m[0], b = m[1], cc = m[2], d = m[3], e = m[4], f = m[5], g = m[6], h = m[7], i = m[8];
+    const double det = a * (e * i - f * h) - b * (d * i - f * g) + cc * (d * h - e * g);
+    if (det == 0.0) return false;
+    const double id = 1.0 / det;
+    o[0] = (e * i - f * h) * id; o[1] = (cc * h - b * i) * id; o[2] = (b * f - cc * e) * id;
+    o[3] = (f * g - d * i) * id; o[4] = (a * i - cc * g) * id; o[5] = (cc * d - a * f) * id;
+    o[6] = (d * h - e * g) * id; o[7] = (b * g - a * h) * id; o[8] = (a * e - b * d) * id;
+    return true;
+}
+
+int pc_synth_render_rgb8(pc_ctx* c, const double H[9], uint8_t* rgb_dev, size_t stride) {
+    PC_CUDA(c, cudaSetDevice(c->device));
+    if (!c->tex) return fail(c, PC_ERR_STATE, "no texture set");
+    double Hi[9];
+    if (!invert3x3(H, Hi)) return fail(c, PC_ERR_INVALID, "singular homography");
+    launch_synth_warp(c->tex, c->tex_w, c->tex_h, c->tex_pitch, Hi, rgb_dev, stride, c->compute);
+    return check_launch(c, "synth", 1);
+}
+
+int pc_device_alloc(pc_ctx* c, size_t bytes, void** out) {
+    PC_CUDA(c, cudaSetDevice(c->device));
+    PC_CUDA(c, cudaMalloc(out, bytes));
+    return PC_OK;
+}
+int pc_device_free(pc_ctx* c, void* p) {
+    PC_CUDA(c, cudaSetDevice(c->device));
+    PC_CUDA(c, cudaFree(p));
+    return PC_OK;
+}
+int pc_host_alloc_pinned(pc_ctx* c, size_t bytes, void** out) {
+    PC_CUDA(c, cudaSetDevice(c->device));
+    PC_CUDA(c, cudaMallocHost(out, bytes));
+    return PC_OK;
+}
+int pc_host_free_pinned(pc_ctx* c, void* p) {
+    PC_CUDA(c, cudaFreeHost(p));
+    return PC_OK;
+}
+int pc_memcpy_d2h(pc_ctx* c, void* dst, const void* src, size_t bytes) {
+    PC_CUDA(c, cudaSetDevice(c->device));
+    PC_CUDA(c, cudaStreamSynchronize(c->compute));
+    PC_CUDA(c, cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
+    return PC_OK;
+}
+int pc_memcpy_h2d(pc_ctx* c, void* dst, const void* src, size_t bytes) {
+    PC_CUDA(c, cudaSetDevice(c->device));
+    PC_CUDA(c, cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice));
+    return PC_OK;
+}
+
+int pc_timing_enable(pc_ctx* c, int on) {
+    c->timing = on != 0;
+    return PC_OK;
+}
+
+int pc_timing_read(pc_ctx* c, pc_kernel_times* out, int reset) {
+    int rc = pc_synchronize(c);
+    if (rc) return rc;
+    for (auto& sp : c->spans) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, sp.start, sp.stop) == cudaSuccess) {
+            c->fam_ms[sp.family] += ms;
+            c->fam_n[sp.family] += 1;
+        }
+        c->event_pool.push_back(sp.start);
+        c->event_pool.push_back(sp.stop);
+    }
+    cudaGetLastError();
+    c->spans.clear();
+    if (out) {
+        out->gray_pyr_ms = c->fam_ms[KF_GRAY_PYR]; out->gray_pyr_n = c->fam_n[KF_GRAY_PYR];
+        out->min_eig_ms = c->fam_ms[KF_MIN_EIG]; out->min_eig_n = c->fam_n[KF_MIN_EIG];
+        out->select_ms = c->fam_ms[KF_SELECT]; out->select_n = c->fam_n[KF_SELECT];
+        out->lk_ms = c->fam_ms[KF_LK]; out->lk_n = c->fam_n[KF_LK];
+        out->compact_ms = c->fam_ms[KF_COMPACT]; out->compact_n = c->fam_n[KF_COMPACT];
+        out->raycast_ms = c->fam_ms[KF_RAYCAST]; out->raycast_n = c->fam_n[KF_RAYCAST];
+        out->pnp_ms = c->fam_ms[KF_PNP]; out->pnp_n = c->fam_n[KF_PNP];
+        out->ba_ms = c->fam_ms[KF_BA]; out->ba_n = c->fam_n[KF_BA];
+    }
+    if (reset) {
+        for (int i = 0; i < KF_COUNT; i++) { c->fam_ms[i] = 0; c->fam_n[i] = 0; }
+    }
+    return PC_OK;
+}
+
+}  // extern "C"

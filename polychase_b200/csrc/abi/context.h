@@ -1,0 +1,144 @@
+// pc_ctx: device, streams, resident frame ring and scratch buffers behind the C ABI.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <deque>
+#include <memory>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../../include/polychase_b200.h"
+#include "../kernels/kernels.h"
+
+namespace pc {
+
+struct FrameSlot {
+    bool used = false;
+    int32_t frame_id = 0;
+    uint64_t stamp = 0;
+    int w = 0, h = 0, levels = 0;
+    Image8 level[kMaxLevels];     // allocated once at the context's max size
+    float* kps = nullptr;         // device, max_features x 2
+    int* n_kps = nullptr;         // device count
+    int* n_accepted = nullptr;    // device: kept corners before the max_corners cut
+    int* greedy_remaining = nullptr;
+    int n_kps_host = -1;          // -1 = not known on host yet
+    bool has_kps = false;
+};
+
+enum KernelFamily { KF_GRAY_PYR = 0, KF_MIN_EIG, KF_SELECT, KF_LK, KF_COMPACT, KF_RAYCAST, KF_PNP, KF_BA, KF_COUNT };
+
+struct TimedSpan {
+    int family;
+    cudaEvent_t start, stop;
+};
+
+struct PairOut {              // compacted LK rows of one pair (device) + pinned mirror
+    uint32_t* idx = nullptr;
+    float* tgt = nullptr;
+    float* err = nullptr;
+    int* count = nullptr;
+};
+
+struct Stage {                // one in-flight frame of the streaming analyzer
+    uint8_t* rgb_dev = nullptr;       // staging for host-provided frames
+    size_t rgb_bytes = 0;
+    PairOut dev[8], host[8];
+    int32_t from[8], to[8];
+    int num_pairs = 0;
+    float* kps_host = nullptr;        // pinned
+    int* counts_host = nullptr;       // pinned: [0]=n_kps [1]=n_accepted [2]=greedy_remaining
+    int32_t frame_id = 0;
+    cudaEvent_t uploaded = nullptr, gray_done = nullptr, computed = nullptr, downloaded = nullptr;
+    bool busy = false;
+    bool gray_pending = false;
+};
+
+struct MeshData;   // track.cu
+struct BAData;     // ba.cu
+
+}  // namespace pc
+
+struct pc_ctx {
+    pc_limits lim{};
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t compute = nullptr, h2d = nullptr, d2h = nullptr;
+    std::string err;
+    uint64_t launches = 0;
+    uint64_t stamp = 0;
+
+    std::vector<pc::FrameSlot> slots;
+
+    // detector scratch (one compute stream -> one set)
+    float* eig = nullptr; int eig_pitch = 0;
+    uint8_t* state = nullptr; int state_pitch = 0;
+    int* cell_max = nullptr; int cell_cap = 0;
+    unsigned long long* cand = nullptr; int cand_cap = 0; int* cand_count = nullptr;
+    pc::SelectWorkspace sel{};
+
+    // LK dense scratch: [8][cap]
+    float* lk_next = nullptr; uint8_t* lk_status = nullptr; float* lk_err = nullptr;
+    pc::PairOut sync_out;           // outputs of the synchronous pc_lk_pair
+    uint8_t* rgb_scratch = nullptr; size_t rgb_scratch_bytes = 0;   // synchronous uploads
+
+    // streaming analyzer
+    bool analyzing = false;
+    pc_video_info vinfo{};
+    pc_gftt_opts gopts{};
+    pc_flow_opts fopts{};
+    std::vector<pc::Stage> stages;
+    std::deque<int> inflight;       // stage indices in push order
+    int next_stage = 0;
+    int32_t last_pushed = 0; bool any_pushed = false;
+    std::unordered_map<int32_t, std::vector<float>> preset_kps;
+
+    // synthetic texture
+    uint8_t* tex = nullptr; int tex_w = 0, tex_h = 0, tex_pitch = 0;
+
+    // timing
+    bool timing = false;
+    std::vector<pc::TimedSpan> spans;
+    std::vector<cudaEvent_t> event_pool;
+    double fam_ms[pc::KF_COUNT] = {0};
+    uint64_t fam_n[pc::KF_COUNT] = {0};
+
+    // track / refine state
+    pc::MeshData* mesh = nullptr;
+    pc::BAData* ba = nullptr;
+
+    ~pc_ctx();
+};
+
+namespace pc {
+
+// Set ctx->err and return `code`.
+int fail(pc_ctx* c, int code, const std::string& msg);
+int cuda_fail(pc_ctx* c, cudaError_t e, const char* what, const char* file, int line);
+void set_global_error(const std::string& msg);
+
+#define PC_CUDA(ctx, expr)                                                         \
+    do {                                                                           \
+        cudaError_t e__ = (expr);                                                  \
+        if (e__ != cudaSuccess) return ::pc::cuda_fail(ctx, e__, #expr, __FILE__, __LINE__); \
+    } while (0)
+
+#define PC_CHECK(ctx, cond, msg)                                                   \
+    do {                                                                           \
+        if (!(cond)) return ::pc::fail(ctx, PC_ERR_INVALID, std::string("check failed: ") + #cond + " -- " + (msg)); \
+    } while (0)
+
+// RAII-ish timing span helpers (no-ops unless ctx->timing)
+void span_begin(pc_ctx* c, int family, cudaStream_t s);
+void span_end(pc_ctx* c, cudaStream_t s);
+int check_launch(pc_ctx* c, const char* what, int n_kernels);
+
+FrameSlot* find_slot(pc_ctx* c, int32_t frame_id);
+PyramidView view_of(const FrameSlot& f);
+
+void free_mesh(MeshData*);
+void free_ba(BAData*);
+
+}  // namespace pc

@@ -1,0 +1,88 @@
+// Internal launcher interface between the C ABI (csrc/abi) and the sm_100a kernels.
+// Everything here takes raw device pointers and a stream; no ownership.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace pc {
+
+constexpr int kMaxLevels = 6;
+
+struct Image8 {          // one pitched u8 plane in HBM
+    uint8_t* data = nullptr;
+    int w = 0, h = 0;
+    int pitch = 0;       // bytes per row, multiple of 128
+};
+
+struct PyramidView {     // what the LK kernel sees of one frame
+    const uint8_t* data[kMaxLevels];
+    int w[kMaxLevels], h[kMaxLevels], pitch[kMaxLevels];
+    int levels;          // number of levels present (maxLevel + 1)
+};
+
+// ---- K1/K2: RGB->gray and pyrDown (gray_pyr.cu) --------------------------------------
+void launch_rgb_to_gray(const uint8_t* rgb, size_t stride, Image8 gray, cudaStream_t s);
+void launch_copy_gray(const uint8_t* src, size_t stride, Image8 gray, cudaStream_t s);
+void launch_pyr_down(Image8 src, Image8 dst, cudaStream_t s);
+
+// ---- K4/K5: min-eigenvalue map, per-cell max, threshold + NMS (mineig.cu) -------------
+struct DetectGrid {
+    int grid_rows, grid_cols, block_w, block_h;   // gftt.cc:39-43
+};
+// eig: w*h floats (pitch in floats = eig_pitch); cell_max: grid_rows*grid_cols ordered ints
+void launch_min_eig(Image8 gray, float* eig, int eig_pitch, DetectGrid g, int* cell_max, cudaStream_t s);
+// candidates: 64-bit keys (ordered value << 32 | address); state: u8 map (pitch = gray.pitch)
+void launch_nms_candidates(const float* eig, int eig_pitch, int w, int h, DetectGrid g,
+                           const int* cell_max, double quality_level, uint8_t* state, int state_pitch,
+                           unsigned long long* cand, int cand_cap, int* cand_count, cudaStream_t s);
+
+// ---- K6/K7: greedy min-distance suppression + ordering (select.cu) --------------------
+struct SelectWorkspace {
+    unsigned long long* accepted;      // cap entries
+    unsigned long long* sorted;        // cap entries
+    int* accepted_count;               // device int
+    int* round_counters;               // kMaxGreedyRounds ints
+    int* remaining;                    // device int: undecided candidates left (0 = converged)
+    void* cub_temp; size_t cub_temp_bytes;
+    int cap;
+};
+constexpr int kMaxGreedyRounds = 2048;
+size_t select_cub_temp_bytes(int cap);
+// Runs suppression over `cand` (count on device), sorts accepted keys descending and writes
+// min(accepted, max_corners) keypoints (x,y floats) + their count.
+void launch_select(const unsigned long long* cand, const int* cand_count, int cand_cap,
+                   const float* eig, int eig_pitch, uint8_t* state, int state_pitch, int w, int h,
+                   double min_distance, int max_corners, SelectWorkspace ws, float* kps_out,
+                   int kps_cap, int* kps_count, int sm_count, cudaStream_t s);
+
+// ---- K8/K9: pyramidal LK + status compaction (lk.cu) ---------------------------------
+struct LKParams {
+    int win, iters, max_level;
+    double eps;          // already clamped; squared inside
+    double min_eig;
+};
+struct LKPair {
+    PyramidView a, b;            // source / target frame
+    const float* pts;            // source keypoints (x,y)
+    const int* n_pts;            // device count
+    float* next;                 // dense outputs, capacity `cap`
+    uint8_t* status;
+    float* err;
+    // compacted outputs
+    uint32_t* out_idx; float* out_tgt; float* out_err; int* out_count;
+};
+constexpr int kMaxPairsPerLaunch = 8;
+struct LKBatch {
+    LKPair pair[kMaxPairsPerLaunch];
+    int num_pairs;
+    int cap;                     // max points per pair
+};
+void launch_lk(const LKBatch& batch, const LKParams& p, cudaStream_t s);
+void launch_lk_compact(const LKBatch& batch, cudaStream_t s);
+
+// ---- synthetic frame warp (synth.cu) ------------------------------------------------
+void launch_synth_warp(const uint8_t* tex, int w, int h, int tex_pitch, const double Hinv[9],
+                       uint8_t* rgb, size_t stride, cudaStream_t s);
+
+}  // namespace pc

@@ -1,0 +1,145 @@
+"""GPU parity tests of the analyze path (K1-K9) through the C ABI, against the oracle
+restatement (oracle/restate.c, itself pinned bit-exact to cv2 in test_oracle_vs_cv2.py)."""
+import numpy as np
+import pytest
+
+from oracle import restate, synth
+from oracle import gftt as ogftt
+
+pytestmark = pytest.mark.gpu
+
+
+def _u32(a):
+    return np.ascontiguousarray(a).view(np.uint32)
+
+
+@pytest.mark.parametrize("w,h", [(640, 480), (643, 487), (1280, 720), (100, 75)])
+def test_gray_pyramid_bit_exact(ctx_small, w, h):
+    rng = np.random.default_rng(w * 7 + h)
+    rgb = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+    ctx_small.upload_rgb(1, rgb)
+    gray = restate.rgb2gray(rgb)
+    levels = restate.pyramid(gray, 3)
+    n = ctx_small.num_levels(1)
+    assert n == ogftt.num_pyramid_levels(w, h, 10, 3)
+    for L in range(n):
+        got = ctx_small.read_level(1, L)
+        assert got.shape == levels[L].shape
+        assert np.array_equal(got, levels[L]), f"level {L} differs"
+
+
+@pytest.mark.parametrize("w,h", [(640, 480), (643, 487), (1280, 720), (101, 77)])
+def test_min_eig_map(ctx_small, w, h):
+    tex = synth.make_texture(w, h, seed=3)
+    ctx_small.upload_gray(2, tex)
+    got = ctx_small.min_eig_map(2, w, h)
+    want_indep = restate.min_eig(tex, mode=3)     # same op order, 3x3 sums formed independently
+    assert np.array_equal(_u32(got), _u32(want_indep))
+    want_cv = restate.min_eig(tex, mode=1)        # OpenCV's running column sum (bit-exact vs cv2)
+    diff = _u32(got) != _u32(want_cv)
+    assert diff.mean() < 2e-5, f"{diff.sum()} pixels differ from the cv2-exact restatement"
+
+
+@pytest.mark.parametrize("w,h,max_corners", [(640, 480, 0), (1280, 720, 2000), (643, 487, 500), (1920, 1080, 4000)])
+def test_detector_matches_oracle(ctx_small, w, h, max_corners):
+    clip = synth.Clip(w, h, 2, seed=11)
+    g = clip.gray(0)
+    from polychase_b200 import capi
+    ctx_small.upload_gray(3, g)
+    got = ctx_small.detect(3, capi.default_gftt(max_corners=max_corners))
+    eig = restate.min_eig(g, mode=3)
+    want = ogftt.gftt_from_eig(eig, max_corners=max_corners)
+    assert got.shape == want.shape
+    assert np.array_equal(got, want)
+    # and against the cv2-exact eig map: same list unless one of the ~2 ppm pixels matters
+    want_cv = ogftt.gftt_from_eig(restate.min_eig(g, mode=1), max_corners=max_corners)
+    assert np.array_equal(got, want_cv)
+
+
+@pytest.mark.parametrize("w,h,n,skip", [(640, 480, 1500, 4), (1280, 720, 2000, 8), (333, 251, 600, 1)])
+def test_lk_bit_exact(ctx_small, w, h, n, skip):
+    clip = synth.Clip(w, h, skip + 1, seed=5)
+    g1, g2 = clip.gray(0), clip.gray(skip)
+    eig = restate.min_eig(g1, mode=1)
+    pts = ogftt.gftt_from_eig(eig, max_corners=n)
+    rng = np.random.default_rng(0)
+    extra = np.stack([rng.uniform(-3, w + 3, 200), rng.uniform(-3, h + 3, 200)], 1).astype(np.float32)
+    pts = np.concatenate([pts, extra]).astype(np.float32)
+    ctx_small.upload_gray(10, g1)
+    ctx_small.upload_gray(11, g2)
+    ctx_small.set_keypoints(10, pts)
+    nxt, st, err = ctx_small.lk_raw(10, 11)
+    L1, L2 = restate.pyramid(g1, 3), restate.pyramid(g2, 3)
+    nlev = ogftt.num_pyramid_levels(w, h, 10, 3)
+    wn, ws, we = restate.lk(L1[:nlev], L2[:nlev], pts)
+    assert np.array_equal(st, ws)
+    assert np.array_equal(_u32(nxt), _u32(wn))
+    ok = ws == 1
+    assert np.array_equal(_u32(err[ok]), _u32(we[ok]))
+    # the filtered rows the reference stores (opticalflow.cc:139-147)
+    idx, tgt, e = ctx_small.lk_pair(10, 11)
+    assert np.array_equal(idx, np.nonzero(ok)[0].astype(np.uint32))
+    assert np.array_equal(_u32(tgt), _u32(wn[ok]))
+    assert np.array_equal(_u32(e), _u32(we[ok]))
+
+
+def test_lk_other_window_sizes(ctx_small):
+    from polychase_b200 import capi
+    w, h = 320, 240
+    clip = synth.Clip(w, h, 3, seed=9)
+    g1, g2 = clip.gray(0), clip.gray(2)
+    pts = ogftt.gftt_from_eig(restate.min_eig(g1, 1), max_corners=300)
+    ctx_small.upload_gray(20, g1)
+    ctx_small.upload_gray(21, g2)
+    ctx_small.set_keypoints(20, pts)
+    for win, lvl in [(7, 2), (15, 3), (16, 1), (5, 3)]:
+        fo = capi.default_flow(window_size=win, max_level=lvl)
+        ctx_small.upload_gray(20, g1, fo)
+        ctx_small.upload_gray(21, g2, fo)
+        ctx_small.set_keypoints(20, pts)
+        nxt, st, err = ctx_small.lk_raw(20, 21, fo)
+        nlev = ogftt.num_pyramid_levels(w, h, win, lvl)
+        L1, L2 = restate.pyramid(g1, lvl), restate.pyramid(g2, lvl)
+        wn, ws, we = restate.lk(L1[:nlev], L2[:nlev], pts, win=win)
+        assert np.array_equal(st, ws), f"win {win}"
+        assert np.array_equal(_u32(nxt), _u32(wn)), f"win {win}"
+
+
+def test_streaming_analyzer_matches_pairwise(ctx_small):
+    """pc_analyze_* must produce exactly the rows GenerateOpticalFlowDatabase writes:
+    keypoints per frame and the 8F-30 directed pairs (opticalflow.cc:237-316)."""
+    from polychase_b200 import capi
+    w, h, F = 320, 240, 12
+    clip = synth.Clip(w, h, F, seed=21, first_frame=1)
+    go = capi.default_gftt(max_corners=300)
+    frames = {k: clip.rgb(k) for k in range(1, F + 1)}
+    ctx_small.analyze_begin(w, h, 1, F, go)
+    got_kps, got_pairs = {}, {}
+    for k in range(1, F + 1):
+        ctx_small.analyze_push(k, frames[k])
+        if ctx_small.analyze_pending() >= 3:
+            r = ctx_small.analyze_pop()
+            got_kps[r["frame_id"]] = r["keypoints"]
+            for (a, b, rows, idx, tgt, err) in r["pairs"]:
+                got_pairs[(a, b)] = (idx, tgt, err)
+    while ctx_small.analyze_pending():
+        r = ctx_small.analyze_pop()
+        got_kps[r["frame_id"]] = r["keypoints"]
+        for (a, b, rows, idx, tgt, err) in r["pairs"]:
+            got_pairs[(a, b)] = (idx, tgt, err)
+    ctx_small.analyze_end()
+    assert len(got_kps) == F
+    expect_pairs = [(a, a + d) for a in range(1, F + 1) for d in (-8, -4, -2, -1, 1, 2, 4, 8) if 1 <= a + d <= F]
+    assert sorted(got_pairs) == sorted(expect_pairs)
+    grays = {k: restate.rgb2gray(frames[k]) for k in frames}
+    pyr = {k: restate.pyramid(grays[k], 3) for k in frames}
+    for k in frames:
+        want = ogftt.gftt_from_eig(restate.min_eig(grays[k], 3), max_corners=300)
+        assert np.array_equal(got_kps[k], want)
+    for (a, b) in expect_pairs:
+        wn, ws, we = restate.lk(pyr[a], pyr[b], got_kps[a])
+        ok = ws == 1
+        idx, tgt, err = got_pairs[(a, b)]
+        assert np.array_equal(idx, np.nonzero(ok)[0].astype(np.uint32))
+        assert np.array_equal(_u32(tgt), _u32(wn[ok]))
+        assert np.array_equal(_u32(err), _u32(we[ok]))
