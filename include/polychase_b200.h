@@ -202,6 +202,10 @@ PC_API int pc_analyze_preset_keypoints(pc_ctx*, int32_t frame_id, const float* k
  * fetched (pointers NULL): results stay device resident. */
 PC_API int pc_analyze_pop(pc_ctx*, pc_frame_result* out, int download);
 PC_API int pc_analyze_pending(pc_ctx*);
+/* Multi-GPU sharding: the first `halo_frames` frames pushed after
+ * pc_analyze_begin are prepared and detected but emit no pair rows -- they are the previous
+ * shard's last frames, needed only as partners of this shard's pairs. */
+PC_API int pc_analyze_set_halo(pc_ctx*, int halo_frames);
 PC_API int pc_analyze_end(pc_ctx*);
 
 /* ---- synthetic frames (bench/test input generator; not on the reference path) --------
@@ -222,6 +226,10 @@ typedef struct pc_kernel_times {
     uint64_t gray_pyr_n, min_eig_n, select_n, lk_n, compact_n, raycast_n, pnp_n, ba_n;
 } pc_kernel_times;
 PC_API int pc_timing_enable(pc_ctx*, int on);
+/* Whole-region device timing: pc_mark joins the context's three streams and records CUDA
+ * event `slot` (0..7) after all work enqueued so far; pc_elapsed_ms waits for both events. */
+PC_API int pc_mark(pc_ctx*, int slot);
+PC_API int pc_elapsed_ms(pc_ctx*, int slot_begin, int slot_end, float* ms_out);
 PC_API int pc_timing_read(pc_ctx*, pc_kernel_times* out, int reset);
 
 /* ---- mesh + track (tracker.cc:36-213, ray_casting.cc:65-133, pnp/) ------------------ */

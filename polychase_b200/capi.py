@@ -132,6 +132,9 @@ SIGNATURES = {
     "pc_analyze_pop": (C.c_int, [C.c_void_p, C.POINTER(FrameResult), C.c_int]),
     "pc_analyze_pending": (C.c_int, [C.c_void_p]),
     "pc_analyze_end": (C.c_int, [C.c_void_p]),
+    "pc_analyze_set_halo": (C.c_int, [C.c_void_p, C.c_int]),
+    "pc_mark": (C.c_int, [C.c_void_p, C.c_int]),
+    "pc_elapsed_ms": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_float)]),
     "pc_synth_set_texture": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
     "pc_synth_render_rgb8": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.c_void_p, C.c_size_t]),
     "pc_device_alloc": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]),
@@ -366,6 +369,17 @@ class Context:
                 idx = tgt = err = None
             out["pairs"].append((p.image_id_from, p.image_id_to, p.rows, idx, tgt, err))
         return out
+
+    def analyze_set_halo(self, n: int):
+        self._chk(self.lib.pc_analyze_set_halo(self.h, n))
+
+    def mark(self, slot: int):
+        self._chk(self.lib.pc_mark(self.h, slot))
+
+    def elapsed_ms(self, a: int, b: int) -> float:
+        ms = C.c_float()
+        self._chk(self.lib.pc_elapsed_ms(self.h, a, b, C.byref(ms)))
+        return float(ms.value)
 
     def analyze_end(self):
         self._chk(self.lib.pc_analyze_end(self.h))

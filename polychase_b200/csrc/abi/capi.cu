@@ -254,6 +254,9 @@ pc_ctx::~pc_ctx() {
     cudaFree(tex);
     for (auto& sp : spans) { cudaEventDestroy(sp.start); cudaEventDestroy(sp.stop); }
     for (auto e : event_pool) cudaEventDestroy(e);
+    for (auto e : marks) if (e) cudaEventDestroy(e);
+    if (join_a) cudaEventDestroy(join_a);
+    if (join_b) cudaEventDestroy(join_b);
     if (mesh) free_mesh(mesh);
     if (ba) free_ba(ba);
     if (compute) cudaStreamDestroy(compute);
@@ -635,6 +638,8 @@ int pc_analyze_begin(pc_ctx* c, const pc_video_info* vi, const pc_gftt_opts* go,
     c->inflight.clear();
     c->next_stage = 0;
     c->any_pushed = false;
+    c->halo_frames = 0;
+    c->pushed_count = 0;
     c->preset_kps.clear();
     for (auto& st : c->stages) { st.busy = false; st.gray_pending = false; }
     c->analyzing = true;
@@ -650,6 +655,37 @@ int pc_analyze_preset_keypoints(pc_ctx* c, int32_t frame_id, const float* kps, i
 }
 
 int pc_analyze_pending(pc_ctx* c) { return (int)c->inflight.size(); }
+
+int pc_analyze_set_halo(pc_ctx* c, int halo_frames) {
+    if (!c->analyzing) return fail(c, PC_ERR_STATE, "no analyze pass is open");
+    PC_CHECK(c, halo_frames >= 0 && !c->any_pushed, "set the halo before the first push");
+    c->halo_frames = halo_frames;
+    return PC_OK;
+}
+
+int pc_mark(pc_ctx* c, int slot) {
+    PC_CUDA(c, cudaSetDevice(c->device));
+    PC_CHECK(c, slot >= 0 && slot < 8, "mark slot must be in [0,8)");
+    if (!c->join_a) {
+        PC_CUDA(c, cudaEventCreateWithFlags(&c->join_a, cudaEventDisableTiming));
+        PC_CUDA(c, cudaEventCreateWithFlags(&c->join_b, cudaEventDisableTiming));
+    }
+    if (!c->marks[slot]) PC_CUDA(c, cudaEventCreate(&c->marks[slot]));
+    PC_CUDA(c, cudaEventRecord(c->join_a, c->h2d));
+    PC_CUDA(c, cudaEventRecord(c->join_b, c->d2h));
+    PC_CUDA(c, cudaStreamWaitEvent(c->compute, c->join_a, 0));
+    PC_CUDA(c, cudaStreamWaitEvent(c->compute, c->join_b, 0));
+    PC_CUDA(c, cudaEventRecord(c->marks[slot], c->compute));
+    return PC_OK;
+}
+
+int pc_elapsed_ms(pc_ctx* c, int a, int b, float* ms_out) {
+    PC_CHECK(c, a >= 0 && a < 8 && b >= 0 && b < 8 && c->marks[a] && c->marks[b] && ms_out, "bad mark slots");
+    PC_CUDA(c, cudaEventSynchronize(c->marks[a]));
+    PC_CUDA(c, cudaEventSynchronize(c->marks[b]));
+    PC_CUDA(c, cudaEventElapsedTime(ms_out, c->marks[a], c->marks[b]));
+    return PC_OK;
+}
 
 int pc_analyze_push_frame(pc_ctx* c, int32_t frame_id, const uint8_t* rgb, size_t stride, int mem_kind) {
     PC_CUDA(c, cudaSetDevice(c->device));
@@ -712,7 +748,9 @@ int pc_analyze_push_frame(pc_ctx* c, int32_t frame_id, const uint8_t* rgb, size_
     if (c->gopts.max_corners > 0) batch.cap = std::min(batch.cap, c->gopts.max_corners);
     static const int kSkips[4] = {1, 2, 4, 8};   // |image_skips|, opticalflow.cc:76-77
     int np = 0;
-    for (int k = 0; k < 4; k++) {
+    const bool is_halo = c->pushed_count < c->halo_frames;
+    c->pushed_count++;
+    for (int k = 0; k < 4 && !is_halo; k++) {
         const int32_t other = frame_id - kSkips[k];
         if (other < first) continue;
         FrameSlot* o = find_slot(c, other);

@@ -93,6 +93,8 @@ struct pc_ctx {
     std::deque<int> inflight;       // stage indices in push order
     int next_stage = 0;
     int32_t last_pushed = 0; bool any_pushed = false;
+    int halo_frames = 0, pushed_count = 0;
+    cudaEvent_t marks[8] = {nullptr}; cudaEvent_t join_a = nullptr, join_b = nullptr;
     std::unordered_map<int32_t, std::vector<float>> preset_kps;
 
     // synthetic texture
