@@ -289,6 +289,9 @@ PC_API int pc_ba_cost(pc_ctx*, const pc_camera_state* traj, const pc_bundle_opts
  * p = 6 or 9); Jtr: num_frames*p.  Either may be NULL. */
 PC_API int pc_ba_normal_equations(pc_ctx*, const pc_camera_state* traj, const pc_bundle_opts*,
                                   float* JtJ_blocks, float* Jtr);
+/* The per-(frame, keypoint) primitive-id cache of RefinementProblemBase (refiner.cc:235-242,
+ * 547-559), in the order of pc_ba_problem.keypoints; 0xFFFFFFFF = no intersection cached. */
+PC_API int pc_ba_read_cache(pc_ctx*, uint32_t* out, int cap);
 typedef int (*pc_ba_iter_cb)(const pc_bundle_stats*, void* user);
 /* LevMarqSparseSolve over the loaded problem, lev_marq.h:492-588; traj is in/out. */
 PC_API int pc_ba_solve(pc_ctx*, const pc_bundle_opts*, pc_camera_state* traj, pc_bundle_stats* stats,

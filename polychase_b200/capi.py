@@ -152,6 +152,7 @@ SIGNATURES = {
     "pc_ba_load": (C.c_int, [C.c_void_p, C.POINTER(BAProblem)]),
     "pc_ba_cost": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(BundleOpts), C.POINTER(C.c_float)]),
     "pc_ba_normal_equations": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(BundleOpts), C.c_void_p, C.c_void_p]),
+    "pc_ba_read_cache": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "pc_ba_solve": (C.c_int, [C.c_void_p, C.POINTER(BundleOpts), C.c_void_p, C.POINTER(BundleStats), BA_ITER_CB, C.c_void_p]),
 }
 
@@ -431,3 +432,162 @@ class Context:
         t = KernelTimes()
         self._chk(self.lib.pc_timing_read(self.h, C.byref(t), 1 if reset else 0))
         return {n: getattr(t, n) for n, _ in KernelTimes._fields_}
+
+
+# ---- track / refine wrappers (methods added to Context) --------------------------------------
+def _ctx_mesh_set(self, verts: np.ndarray, tris: np.ndarray, mask_bits: Optional[np.ndarray] = None):
+    verts = np.ascontiguousarray(verts, np.float32).reshape(-1, 3)
+    tris = np.ascontiguousarray(tris, np.uint32).reshape(-1, 3)
+    mb = None if mask_bits is None or len(mask_bits) == 0 else np.ascontiguousarray(mask_bits, np.uint32)
+    self._chk(self.lib.pc_mesh_set(self.h, _ptr(verts), len(verts), _ptr(tris), len(tris), _ptr(mb),
+                                   0 if mb is None else len(mb)))
+
+
+def _ctx_ray_cast(self, model: np.ndarray, cam: CameraState, pos: np.ndarray, check_mask: bool = True):
+    model = np.ascontiguousarray(model, np.float32).reshape(16)
+    pos = np.ascontiguousarray(pos, np.float32).reshape(-1, 2)
+    n = len(pos)
+    hit = np.zeros(n, np.uint8)
+    P = np.zeros((n, 3), np.float32)
+    prim = np.zeros(n, np.uint32)
+    uv = np.zeros((n, 2), np.float32)
+    t = np.zeros(n, np.float32)
+    self._chk(self.lib.pc_ray_cast(self.h, _ptr(model), C.byref(cam), _ptr(pos), n, 1 if check_mask else 0,
+                                   _ptr(hit), _ptr(P), _ptr(prim), _ptr(uv), _ptr(t)))
+    return hit.astype(bool), P, prim, uv, t
+
+
+def _ctx_solve_pnp(self, X, x, cam: CameraState, opts: Optional[BundleOpts] = None, weights=None,
+                   max_inlier_error: float = 12.0, opt_f: bool = False, opt_pp: bool = False):
+    X = np.ascontiguousarray(X, np.float32).reshape(-1, 3)
+    x = np.ascontiguousarray(x, np.float32).reshape(-1, 2)
+    w = None if weights is None else np.ascontiguousarray(weights, np.float32)
+    opts = opts or default_bundle()
+    out = CameraState.from_buffer_copy(cam)
+    st = BundleStats()
+    inl = C.c_float()
+    self._chk(self.lib.pc_solve_pnp(self.h, _ptr(X), _ptr(x), _ptr(w), len(X), C.byref(opts), max_inlier_error,
+                                    int(opt_f), int(opt_pp), C.byref(out), C.byref(st), C.byref(inl)))
+    return out, st, float(inl.value)
+
+
+def _ctx_track_frame(self, sources, model, init: CameraState, opts: Optional[BundleOpts] = None,
+                     opt_f: bool = False, opt_pp: bool = False):
+    """sources: list of (CameraState, keypoints (nk,2), src_idx (rows,), tgt (rows,2))."""
+    opts = opts or default_bundle()
+    model = np.ascontiguousarray(model, np.float32).reshape(16)
+    arr = (MatchSource * max(len(sources), 1))()
+    keep = []
+    for i, (cam, kps, idx, tgt) in enumerate(sources):
+        kps = np.ascontiguousarray(kps, np.float32).reshape(-1, 2)
+        idx = np.ascontiguousarray(idx, np.uint32)
+        tgt = np.ascontiguousarray(tgt, np.float32).reshape(-1, 2)
+        keep += [kps, idx, tgt]
+        arr[i] = MatchSource(cam, kps.ctypes.data, len(kps), idx.ctypes.data, tgt.ctypes.data, len(idx))
+    out = CameraState()
+    st = BundleStats()
+    inl = C.c_float()
+    nm = C.c_int()
+    self._chk(self.lib.pc_track_frame(self.h, arr, len(sources), _ptr(model), C.byref(init), C.byref(opts),
+                                      int(opt_f), int(opt_pp), C.byref(out), C.byref(st), C.byref(inl), C.byref(nm)))
+    return out, st, float(inl.value), nm.value
+
+
+def _ctx_ba_load(self, keypoints, edges, model, opt_f: bool = False, opt_pp: bool = False):
+    """keypoints: list of (n_i,2) per frame; edges: list of (src, tgt, src_idx, tgt_kps)."""
+    offs = np.concatenate([[0], np.cumsum([len(k) for k in keypoints])]).astype(np.int32)
+    kps = (np.concatenate([np.asarray(k, np.float32).reshape(-1, 2) for k in keypoints])
+           if offs[-1] else np.zeros((0, 2), np.float32))
+    kps = np.ascontiguousarray(kps, np.float32)
+    ed = (BAEdge * max(len(edges), 1))()
+    idx_all, tgt_all = [], []
+    row = 0
+    for i, (s, t, idx, tgt) in enumerate(edges):
+        ed[i] = BAEdge(int(s), int(t), row, len(idx))
+        idx_all.append(np.asarray(idx, np.uint32))
+        tgt_all.append(np.asarray(tgt, np.float32).reshape(-1, 2))
+        row += len(idx)
+    idx_all = np.ascontiguousarray(np.concatenate(idx_all) if idx_all else np.zeros(0, np.uint32), np.uint32)
+    tgt_all = np.ascontiguousarray(np.concatenate(tgt_all) if tgt_all else np.zeros((0, 2), np.float32), np.float32)
+    pr = BAProblem()
+    pr.num_frames = len(keypoints)
+    pr.kp_offsets = offs.ctypes.data
+    pr.keypoints = kps.ctypes.data
+    pr.num_edges = len(edges)
+    pr.edges = C.addressof(ed)
+    pr.src_kps_indices = idx_all.ctypes.data
+    pr.tgt_kps = tgt_all.ctypes.data
+    pr.model[:] = [float(v) for v in np.asarray(model, np.float32).reshape(16)]
+    pr.optimize_focal_length = int(opt_f)
+    pr.optimize_principal_point = int(opt_pp)
+    self._chk(self.lib.pc_ba_load(self.h, C.byref(pr)))
+    self._ba_nf = len(keypoints)
+    self._ba_p = 9 if (opt_f or opt_pp) else 6
+
+
+def _traj_array(traj):
+    arr = (CameraState * len(traj))()
+    for i, c in enumerate(traj):
+        arr[i] = c
+    return arr
+
+
+def _ctx_ba_cost(self, traj, opts: Optional[BundleOpts] = None) -> float:
+    opts = opts or default_bundle()
+    arr = _traj_array(traj)
+    cost = C.c_float()
+    self._chk(self.lib.pc_ba_cost(self.h, arr, C.byref(opts), C.byref(cost)))
+    return float(cost.value)
+
+
+def _ctx_ba_normal_equations(self, traj, opts: Optional[BundleOpts] = None):
+    opts = opts or default_bundle()
+    arr = _traj_array(traj)
+    nf, p = self._ba_nf, self._ba_p
+    band = np.zeros((nf, 9, p, p), np.float32)
+    jtr = np.zeros((nf * p,), np.float32)
+    self._chk(self.lib.pc_ba_normal_equations(self.h, arr, C.byref(opts), _ptr(band), _ptr(jtr)))
+    return band, jtr
+
+
+def _ctx_ba_solve(self, traj, opts: Optional[BundleOpts] = None, callback=None):
+    opts = opts or default_bundle()
+    arr = _traj_array(traj)
+    st = BundleStats()
+    if callback is not None:
+        cb = BA_ITER_CB(lambda s, u: 1 if callback(s.contents) else 0)
+    else:
+        cb = C.cast(None, BA_ITER_CB)
+    self._chk(self.lib.pc_ba_solve(self.h, C.byref(opts), arr, C.byref(st), cb, None))
+    return [CameraState.from_buffer_copy(arr[i]) for i in range(len(traj))], st
+
+
+def _ctx_ba_read_cache(self, n: int) -> np.ndarray:
+    out = np.zeros(n, np.uint32)
+    self._chk(self.lib.pc_ba_read_cache(self.h, _ptr(out), n))
+    return out
+
+
+def band_to_dense(band: np.ndarray) -> np.ndarray:
+    """Lower-triangular dense matrix from the (nf, 9, p, p) band layout of pc_ba_normal_equations."""
+    nf, nb, p, _ = band.shape
+    A = np.zeros((nf * p, nf * p), band.dtype)
+    for i in range(nf):
+        for k in range(nb):
+            j = i - k
+            if j < 0:
+                continue
+            blk = band[i, k]
+            A[i * p:(i + 1) * p, j * p:(j + 1) * p] = np.tril(blk) if k == 0 else blk
+    return A
+
+
+Context.mesh_set = _ctx_mesh_set
+Context.ray_cast = _ctx_ray_cast
+Context.solve_pnp = _ctx_solve_pnp
+Context.track_frame = _ctx_track_frame
+Context.ba_load = _ctx_ba_load
+Context.ba_cost = _ctx_ba_cost
+Context.ba_normal_equations = _ctx_ba_normal_equations
+Context.ba_solve = _ctx_ba_solve
+Context.ba_read_cache = _ctx_ba_read_cache
