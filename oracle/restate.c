@@ -85,7 +85,7 @@ void orc_scharr(const uint8_t* src, int w, int h, int16_t* d) {
 
 /* A.4: cornerMinEigenVal(u8, blockSize=3, ksize=3), REFLECT_101.
  * mode bit0: 1 = AVX2-dispatched Sobel op order (what cv2 / the reference wheel run on
- *            x86-64: FMA everywhere except the w%16 tail columns of the row-smoothing
+ *            x86-64: FMA everywhere except the w%32 tail columns of the row-smoothing
  *            filter, which are plain mul+add), 0 = plain C++ op order (cv::setUseOptimized(false)).
  * mode bit1: 0 = 3x3 box sums exactly as OpenCV's ColumnSum<double,float> forms them: a
  *            running double sum per column, SUM += row[y+1]; out = (float)SUM;
@@ -96,9 +96,9 @@ void orc_min_eig(const uint8_t* src, int w, int h, int mode, float* eig) {
     const float s = (float)(1.0 / (4.0 * 3.0 * 255.0));
     const float s2 = 2.0f * s;
     const int fma_mode = mode & 1, indep_box = (mode >> 1) & 1;
-    /* measured against cv2 4.13.0: the row filter's vector body covers 16 columns per
-     * step and its w%16 tail is plain mul+add; the column filter is fused everywhere. */
-    const int wvec = fma_mode ? (w / 16) * 16 : 0;
+    /* measured against cv2 4.13.0: the row filter's vector body covers 32 columns per
+     * step and its w%32 tail is plain mul+add; the column filter is fused everywhere. */
+    const int wvec = fma_mode ? (w / 32) * 32 : 0;
     const size_t n = (size_t)w * h;
     float* rx = (float*)malloc(sizeof(float) * n);   /* p[x+1]-p[x-1] */
     float* rs = (float*)malloc(sizeof(float) * n);   /* row-smoothed */

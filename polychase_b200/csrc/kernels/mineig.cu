@@ -7,7 +7,7 @@
 // that of OpenCV's AVX2-dispatched Sobel (what an x86-64 build of the reference runs;
 // SURVEY.md Appendix A.4, pinned against cv2 4.13.0 by oracle/restate.c):
 //   rx = p[x+1] - p[x-1]                      dx = fma(rx[y-1] + rx[y+1], s, rx[y] * 2s)
-//   rs = fma(p[x+1], s, fma(p[x], 2s, p[x-1]*s))   (plain mul/add in the w%16 tail columns)
+//   rs = fma(p[x+1], s, fma(p[x], 2s, p[x-1]*s))   (plain mul/add in the w%32 tail columns)
 //   dy = rs[y+1] - rs[y-1]
 //   cov = (dx*dx, dx*dy, dy*dy), 3x3 box sums formed in double and rounded once,
 //   eig = (a + c) - sqrt((a - c)*(a - c) + b*b),  a = Sxx/2, b = Sxy, c = Syy/2, no FMA.
@@ -42,7 +42,7 @@ __global__ void __launch_bounds__(256) min_eig_kernel(const uint8_t* __restrict_
     const int x0 = blockIdx.x * ME_TW, y0 = blockIdx.y * ME_TH;   // tile origin (output coords)
     const float s = (float)(1.0 / (4.0 * 3.0 * 255.0));
     const float s2 = 2.0f * s;
-    const int wvec = (w / 16) * 16;
+    const int wvec = (w / 32) * 32;
 
     // gray region [x0-2, x0+TW+2) x [y0-2, y0+TH+2), reflected at the image borders
     for (int idx = tid; idx < ME_GH * ME_GW; idx += 256) {
