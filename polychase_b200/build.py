@@ -29,13 +29,13 @@ NO_FMAD = {"lk.cu", "mineig.cu"}
 
 
 def sources():
-    return sorted(glob.glob(os.path.join(CSRC, "kernels", "*.cu")) + glob.glob(os.path.join(CSRC, "abi", "*.cu"))
-                  + glob.glob(os.path.join(CSRC, "host", "*.cu")) + glob.glob(os.path.join(CSRC, "host", "*.cc")))
+    # csrc/host is the C++ host layer above the C ABI: it builds into the pybind11 module instead
+    return sorted(glob.glob(os.path.join(CSRC, "kernels", "*.cu")) + glob.glob(os.path.join(CSRC, "abi", "*.cu")))
 
 
 def headers():
     out = []
-    for pat in ("kernels/*.h", "kernels/*.cuh", "abi/*.h", "host/*.h"):
+    for pat in ("kernels/*.h", "kernels/*.cuh", "abi/*.h"):
         out += glob.glob(os.path.join(CSRC, pat))
     out.append(os.path.join(HERE, "..", "include", "polychase_b200.h"))
     return out

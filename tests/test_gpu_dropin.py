@@ -1,0 +1,173 @@
+"""End-to-end drop-in test on the GPU: the addon's call sequence through
+the `polychase_core` surface -- OpticalFlowThread with the frame hand-off -> SQLite ->
+TrackerThread -> RefinerThread -- checked against the oracle."""
+import time
+
+import numpy as np
+import pytest
+
+from oracle import db as odb
+from oracle import gftt as ogftt
+from oracle import pnp as opnp
+from oracle import restate, synth
+from oracle import track as otrack
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+F = np.float32
+
+
+@pytest.fixture(scope="module")
+def core():
+    from polychase_b200 import polychase_core
+    return polychase_core
+
+
+def _pump(thread, on_msg, timeout=120):
+    t0 = time.time()
+    while time.time() - t0 < timeout:
+        m = thread.try_pop()
+        if m is None:
+            time.sleep(0.002)
+            continue
+        if isinstance(m, bool):
+            return
+        on_msg(m)
+    raise TimeoutError
+
+
+def test_analyze_track_refine_like_the_addon(core, tmp_path):
+    w, h, NF, first = 320, 240, 14, 1          # Blender frame numbers are 1-based
+    clip = synth.Clip(w, h, NF, seed=6, first_frame=first)
+    frames = {k: clip.rgb(k) for k in range(first, first + NF)}
+    dbp = str(tmp_path / "clip.db")
+    go = core.GFTTOptions()
+    go.max_corners = 300
+    th = core.OpticalFlowThread(core.VideoInfo(w, h, first, NF), dbp, go)
+    requested, progress, errors = [], [], []
+
+    def on_msg(m):
+        if isinstance(m, core.OpticalFlowRequest):
+            requested.append(m.frame_id)
+            th.provide_frame(m.frame_id, frames[m.frame_id])
+        elif isinstance(m, core.OpticalFlowProgress):
+            progress.append((m.progress, m.progress_message))
+        elif isinstance(m, core.CppException):
+            errors.append(m.what())
+    _pump(th, on_msg)
+    th.join()
+    assert not errors, errors
+    assert requested == list(range(first, first + NF))
+    assert progress[-1][1] == "Done" and progress[0][1] == f"Processing frame {first}"
+
+    # database content == what the reference's loop would have written (oracle restatement)
+    o = odb.Database(dbp)
+    assert o.frames() == list(range(first, first + NF))
+    want_pairs = sorted((a, a + d) for a in range(first, first + NF) for d in (-8, -4, -2, -1, 1, 2, 4, 8)
+                        if first <= a + d < first + NF)
+    assert o.pairs() == want_pairs and len(want_pairs) == 8 * NF - 30
+    grays = {k: restate.rgb2gray(frames[k]) for k in frames}
+    pyr = {k: restate.pyramid(grays[k], 3) for k in frames}
+    kps, flows = {}, {}
+    for k in frames:
+        kps[k] = o.read_keypoints(k)
+        assert np.array_equal(kps[k], ogftt.gftt_from_eig(restate.min_eig(grays[k], 3), max_corners=300))
+    for (a, b) in want_pairs:
+        idx, tgt, err = o.read_image_pair_flow(a, b)
+        wn, ws, we = restate.lk(pyr[a], pyr[b], kps[a])
+        ok = ws == 1
+        assert np.array_equal(idx, np.nonzero(ok)[0].astype(np.uint32))
+        assert np.array_equal(tgt.view(np.uint32), wn[ok].view(np.uint32))
+        assert np.array_equal(err.view(np.uint32), we[ok].view(np.uint32))
+        flows[(a, b)] = (idx, tgt, err)
+    # sources come back in ascending image_id_from
+    assert o.find_optical_flows_to_image(first + 9) == sorted(o.find_optical_flows_to_image(first + 9))
+    o.close()
+
+    # resume: a second pass over an already complete database writes nothing new and does not fail
+    th2 = core.OpticalFlowThread(core.VideoInfo(w, h, first, NF), dbp, go)
+    _pump(th2, lambda m: th2.provide_frame(m.frame_id, frames[m.frame_id]) if isinstance(m, core.OpticalFlowRequest)
+          else errors.append(m.what()) if isinstance(m, core.CppException) else None)
+    th2.join()
+    assert not errors, errors
+
+    # ---- track -------------------------------------------------------------------------------
+    verts, tris = H.bumpy_mesh(clip, quads=8, amp=0.03)
+    mesh = core.AcceleratedMesh(verts, tris)
+    K = clip.K
+    intr = core.CameraIntrinsics(K["fx"], K["fy"], K["cx"], K["cy"], 1.0, w, h, core.CameraConvention.OpenCV)
+    view = np.eye(4, dtype=F)
+    view[:3, :3] = clip.R[0]
+    view[:3, 3] = clip.t[0]
+    scene = core.SceneTransformations(np.eye(4, dtype=F), view, intr)
+    bo = core.BundleOptions()
+    bo.loss_type = core.LossType.Cauchy
+    tt = core.TrackerThread(dbp, first, first + NF - 1, scene, mesh, False, False, bo)
+    results = []
+    _pump(tt, lambda m: results.append(m) if isinstance(m, core.FrameTrackingResult) else errors.append(m.what()))
+    tt.join()
+    assert not errors, errors
+    assert [r.frame for r in results] == list(range(first + 1, first + NF))
+    start = H.oracle_cam(clip, first)
+    # the start pose goes through Pose::FromRt(view_matrix) in both implementations
+    want = otrack.track_sequence(kps, flows, first, first + NF - 1, start, np.eye(4, dtype=F), verts, tris, None,
+                                 opnp.BundleOptions(loss_type=opnp.CAUCHY))
+    for r in results:
+        ocam = want[r.frame][0]
+        dq = np.abs(np.abs(np.array(r.pose.q)) - np.abs(ocam.pose.q)).max()
+        dt = np.abs(np.array(r.pose.t) - ocam.pose.t).max() / np.abs(ocam.pose.t).max()
+        assert dq < 1e-4 and dt < 1e-4, (r.frame, dq, dt)
+        assert r.inlier_ratio > 0.9 and r.bundle_stats.cost <= r.bundle_stats.initial_cost
+
+    # ---- refine ------------------------------------------------------------------------------
+    traj = core.CameraTrajectory(first, NF)
+    for k in range(first, first + NF):
+        p = core.Pose()
+        src = H.oracle_cam(clip, k) if k in (first, first + NF - 1) else None
+        if src is None:
+            r = results[k - first - 1]
+            p.q, p.t = r.pose.q, r.pose.t
+        else:
+            p.q, p.t = src.pose.q, src.pose.t
+        traj.set(k, core.CameraState(intr, p))
+    rt = core.RefinerThread(dbp, traj, np.eye(4, dtype=F), mesh, False, False, bo)
+    updates = []
+    _pump(rt, lambda m: updates.append(m) if isinstance(m, core.RefineTrajectoryUpdate) else errors.append(m.what()))
+    rt.join()
+    assert not errors, errors
+    assert updates and updates[-1].message.startswith("Cost: ")
+    assert updates[-1].stats.cost <= updates[-1].stats.initial_cost
+    # the trajectory object was refined in place; ground truth is close
+    for k in range(first + 1, first + NF - 1):
+        got = traj.get(k)
+        gt = H.oracle_cam(clip, k)
+        assert np.abs(np.array(got.pose.t) - gt.pose.t).max() < 5e-3 * clip.depth
+
+
+def test_tracker_thread_reports_errors(core, tmp_path):
+    dbp = str(tmp_path / "empty.db")
+    core.Database(dbp).close()
+    v = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0]], np.float32)
+    mesh = core.AcceleratedMesh(v, np.array([[0, 1, 2]], np.uint32))
+    intr = core.CameraIntrinsics(100, 100, 50, 50, 1.0, 100, 100, core.CameraConvention.OpenCV)
+    scene = core.SceneTransformations(np.eye(4, dtype=F), np.eye(4, dtype=F), intr)
+    tt = core.TrackerThread(dbp, 1, 3, scene, mesh, False, False, core.BundleOptions())
+    msgs = []
+    _pump(tt, msgs.append)
+    tt.join()
+    assert len(msgs) == 1 and isinstance(msgs[0], core.CppException)
+    assert "Not enough features" in msgs[0].what()          # tracker.cc:162-166 (message preserved, not sliced)
+
+
+def test_optical_flow_thread_cancel(core, tmp_path):
+    th = core.OpticalFlowThread(core.VideoInfo(64, 48, 1, 100), str(tmp_path / "c.db"))
+    time.sleep(0.05)
+    th.request_stop()
+    th.join()
+    last = None
+    while True:
+        m = th.try_pop()
+        if m is None:
+            break
+        last = m
+    assert last is True
