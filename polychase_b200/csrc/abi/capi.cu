@@ -162,7 +162,7 @@ static int run_detector(pc_ctx* c, FrameSlot* f, const pc_gftt_opts* go, cudaStr
     span_end(c, s);
     span_begin(c, KF_SELECT, s);
     launch_nms_candidates(c->eig, c->eig_pitch, f->w, f->h, g, c->cell_max, go->quality_level, c->state,
-                          c->state_pitch, c->cand, c->cand_cap, c->cand_count, s);
+                          c->state_pitch, c->cand, c->cand_cap, c->cand_count, c->sel.hist, s);
     SelectWorkspace ws = c->sel;
     ws.accepted_count = f->n_accepted;
     ws.remaining = f->greedy_remaining;
@@ -171,7 +171,7 @@ static int run_detector(pc_ctx* c, FrameSlot* f, const pc_gftt_opts* go, cudaStr
     span_end(c, s);
     f->has_kps = true;
     f->n_kps_host = -1;
-    return check_launch(c, "detector", 6);
+    return check_launch(c, "detector", go->max_corners > 0 ? 10 : 6);
 }
 
 static LKParams make_lk_params(const pc_flow_opts* fo) {
@@ -239,6 +239,7 @@ pc_ctx::~pc_ctx() {
     }
     cudaFree(eig); cudaFree(state); cudaFree(cell_max); cudaFree(cand); cudaFree(cand_count);
     cudaFree(sel.accepted); cudaFree(sel.sorted); cudaFree(sel.round_counters); cudaFree(sel.cub_temp);
+    cudaFree(sel.strong); cudaFree(sel.topk); cudaFree(sel.hist); cudaFree(sel.sel);
     cudaFree(lk_next); cudaFree(lk_status); cudaFree(lk_err);
     free_pair_out(sync_out, false);
     cudaFree(rgb_scratch);
@@ -340,6 +341,7 @@ int pc_create(const pc_limits* limits, pc_ctx** out) {
             lw = (lw + 1) / 2; lh = (lh + 1) / 2;
         }
         uint8_t* base = nullptr;
+        total += 256;   // lk10.cu stages patches with 4-byte loads that may run a few bytes past a row
         PC_CUDA(nullptr, cudaMalloc(&base, total));
         for (int L = 0; L < kMaxLevels; L++) { s.level[L].data = base + offs[L]; s.level[L].pitch = pitches[L]; }
         PC_CUDA(nullptr, cudaMalloc(&s.kps, sizeof(float) * 2 * cap));
@@ -361,7 +363,12 @@ int pc_create(const pc_limits* limits, pc_ctx** out) {
     cp->sel.cap = cp->cand_cap;
     PC_CUDA(nullptr, cudaMalloc(&cp->sel.accepted, sizeof(unsigned long long) * cp->cand_cap));
     PC_CUDA(nullptr, cudaMalloc(&cp->sel.sorted, sizeof(unsigned long long) * cp->cand_cap));
-    PC_CUDA(nullptr, cudaMalloc(&cp->sel.round_counters, sizeof(int) * kMaxGreedyRounds));
+    PC_CUDA(nullptr, cudaMalloc(&cp->sel.round_counters, sizeof(int) * 2 * kMaxGreedyRounds));
+    PC_CUDA(nullptr, cudaMalloc(&cp->sel.strong, sizeof(unsigned long long) * cp->cand_cap));
+    cp->sel.topk_cap = cap;
+    PC_CUDA(nullptr, cudaMalloc(&cp->sel.topk, sizeof(unsigned long long) * cap));
+    PC_CUDA(nullptr, cudaMalloc(&cp->sel.hist, sizeof(int) * 65536));
+    PC_CUDA(nullptr, cudaMalloc(&cp->sel.sel, sizeof(int) * 8));
     cp->sel.cub_temp_bytes = select_cub_temp_bytes(cp->cand_cap);
     PC_CUDA(nullptr, cudaMalloc(&cp->sel.cub_temp, cp->sel.cub_temp_bytes));
     PC_CUDA(nullptr, cudaMalloc(&cp->lk_next, sizeof(float) * 2 * (size_t)cap * 8));

@@ -33,19 +33,26 @@ struct DetectGrid {
 // eig: w*h floats (pitch in floats = eig_pitch); cell_max: grid_rows*grid_cols ordered ints
 void launch_min_eig(Image8 gray, float* eig, int eig_pitch, DetectGrid g, int* cell_max, cudaStream_t s);
 // candidates: 64-bit keys (ordered value << 32 | address); state: u8 map (pitch = gray.pitch)
+// value_hist: 4096 bins over the top 12 bits of the ordered candidate value (cleared here)
 void launch_nms_candidates(const float* eig, int eig_pitch, int w, int h, DetectGrid g,
                            const int* cell_max, double quality_level, uint8_t* state, int state_pitch,
-                           unsigned long long* cand, int cand_cap, int* cand_count, cudaStream_t s);
+                           unsigned long long* cand, int cand_cap, int* cand_count, int* value_hist,
+                           cudaStream_t s);
 
 // ---- K6/K7: greedy min-distance suppression + ordering (select.cu) --------------------
 struct SelectWorkspace {
     unsigned long long* accepted;      // cap entries
     unsigned long long* sorted;        // cap entries
+    unsigned long long* strong;        // cap entries: the strongest candidates (max_corners > 0 path)
+    unsigned long long* topk;          // topk_cap entries: the max_corners strongest kept keys
     int* accepted_count;               // device int
-    int* round_counters;               // kMaxGreedyRounds ints
+    int* round_counters;               // 2 * kMaxGreedyRounds ints
     int* remaining;                    // device int: undecided candidates left (0 = converged)
+    int* hist;                         // 4096 ints
+    int* sel;                          // small device scratch: [0] strong threshold (top 16 bits), [1] strong count
     void* cub_temp; size_t cub_temp_bytes;
     int cap;
+    int topk_cap;
 };
 constexpr int kMaxGreedyRounds = 2048;
 size_t select_cub_temp_bytes(int cap);

@@ -327,11 +327,14 @@ void launch_lk_t(const LKBatch& batch, const LKParams& p, cudaStream_t s) {
 
 bool lk_window_supported(int win) { return win >= 3 && win <= 16; }
 
+void launch_lk10(const LKBatch& batch, const LKParams& p, cudaStream_t s);   // lk10.cu
+
 void launch_lk(const LKBatch& batch, const LKParams& p, cudaStream_t s) {
     switch (p.win) {
 #define PC_LK_CASE(W) case W: launch_lk_t<W>(batch, p, s); break;
         PC_LK_CASE(3) PC_LK_CASE(4) PC_LK_CASE(5) PC_LK_CASE(6) PC_LK_CASE(7) PC_LK_CASE(8) PC_LK_CASE(9)
-        PC_LK_CASE(10) PC_LK_CASE(11) PC_LK_CASE(12) PC_LK_CASE(13) PC_LK_CASE(14) PC_LK_CASE(15) PC_LK_CASE(16)
+        case 10: launch_lk10(batch, p, s); break;
+        PC_LK_CASE(11) PC_LK_CASE(12) PC_LK_CASE(13) PC_LK_CASE(14) PC_LK_CASE(15) PC_LK_CASE(16)
 #undef PC_LK_CASE
         default: break;
     }

@@ -149,7 +149,8 @@ __global__ void __launch_bounds__(256) nms_candidates_kernel(const float* __rest
                                                              const int* __restrict__ cell_max, double quality,
                                                              uint8_t* __restrict__ state, int state_pitch,
                                                              unsigned long long* __restrict__ cand, int cand_cap,
-                                                             int* __restrict__ cand_count) {
+                                                             int* __restrict__ cand_count,
+                                                             int* __restrict__ value_hist) {
     const int x = blockIdx.x * 64 + (threadIdx.x & 63);
     const int y = blockIdx.y * 4 + (threadIdx.x >> 6);
     bool is_cand = false;
@@ -190,19 +191,21 @@ __global__ void __launch_bounds__(256) nms_candidates_kernel(const float* __rest
         base = __shfl_sync(0xffffffffu, base, leader);
         if (is_cand) {
             const int slot = base + __popc(mask & ((1u << lane) - 1));
-            if (slot < cand_cap)
-                cand[slot] = ((unsigned long long)float_to_ordered_uint(v) << 32) | (unsigned)(y * w + x);
+            const uint32_t ov = float_to_ordered_uint(v);
+            if (slot < cand_cap) cand[slot] = ((unsigned long long)ov << 32) | (unsigned)(y * w + x);
+            atomicAdd(&value_hist[ov >> 20], 1);
         }
     }
 }
 
 void launch_nms_candidates(const float* eig, int eig_pitch, int w, int h, DetectGrid g, const int* cell_max,
                            double quality_level, uint8_t* state, int state_pitch, unsigned long long* cand,
-                           int cand_cap, int* cand_count, cudaStream_t s) {
+                           int cand_cap, int* cand_count, int* value_hist, cudaStream_t s) {
     cudaMemsetAsync(cand_count, 0, sizeof(int), s);
+    cudaMemsetAsync(value_hist, 0, sizeof(int) * 4096, s);
     dim3 grid((w + 63) / 64, (h + 3) / 4);
     nms_candidates_kernel<<<grid, 256, 0, s>>>(eig, eig_pitch, w, h, g, cell_max, quality_level, state, state_pitch,
-                                               cand, cand_cap, cand_count);
+                                               cand, cand_cap, cand_count, value_hist);
 }
 
 }  // namespace pc
