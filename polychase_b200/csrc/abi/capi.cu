@@ -171,7 +171,7 @@ static int run_detector(pc_ctx* c, FrameSlot* f, const pc_gftt_opts* go, cudaStr
     span_end(c, s);
     f->has_kps = true;
     f->n_kps_host = -1;
-    return check_launch(c, "detector", go->max_corners > 0 ? 10 : 6);
+    return check_launch(c, "detector", go->max_corners > 0 ? 7 : 6);
 }
 
 static LKParams make_lk_params(const pc_flow_opts* fo) {
@@ -239,7 +239,7 @@ pc_ctx::~pc_ctx() {
     }
     cudaFree(eig); cudaFree(state); cudaFree(cell_max); cudaFree(cand); cudaFree(cand_count);
     cudaFree(sel.accepted); cudaFree(sel.sorted); cudaFree(sel.round_counters); cudaFree(sel.cub_temp);
-    cudaFree(sel.strong); cudaFree(sel.topk); cudaFree(sel.hist); cudaFree(sel.sel);
+    cudaFree(sel.strong); cudaFree(sel.kept_hist); cudaFree(sel.hist); cudaFree(sel.sel);
     cudaFree(lk_next); cudaFree(lk_status); cudaFree(lk_err);
     free_pair_out(sync_out, false);
     cudaFree(rgb_scratch);
@@ -362,12 +362,14 @@ int pc_create(const pc_limits* limits, pc_ctx** out) {
     PC_CUDA(nullptr, cudaMalloc(&cp->cand_count, sizeof(int)));
     cp->sel.cap = cp->cand_cap;
     PC_CUDA(nullptr, cudaMalloc(&cp->sel.accepted, sizeof(unsigned long long) * cp->cand_cap));
-    PC_CUDA(nullptr, cudaMalloc(&cp->sel.sorted, sizeof(unsigned long long) * cp->cand_cap));
+    cp->sel.sorted_cap = 1;
+    while (cp->sel.sorted_cap < cp->cand_cap) cp->sel.sorted_cap <<= 1;
+    PC_CUDA(nullptr, cudaMalloc(&cp->sel.sorted, sizeof(unsigned long long) * cp->sel.sorted_cap));
     PC_CUDA(nullptr, cudaMalloc(&cp->sel.round_counters, sizeof(int) * 2 * kMaxGreedyRounds));
     PC_CUDA(nullptr, cudaMalloc(&cp->sel.strong, sizeof(unsigned long long) * cp->cand_cap));
-    cp->sel.topk_cap = cap;
-    PC_CUDA(nullptr, cudaMalloc(&cp->sel.topk, sizeof(unsigned long long) * cap));
-    PC_CUDA(nullptr, cudaMalloc(&cp->sel.hist, sizeof(int) * 65536));
+    PC_CUDA(nullptr, cudaMalloc(&cp->sel.hist, sizeof(int) * 4096));
+    PC_CUDA(nullptr, cudaMalloc(&cp->sel.kept_hist, sizeof(int) * 65536));
+    PC_CUDA(nullptr, cudaMemset(cp->sel.kept_hist, 0, sizeof(int) * 65536));
     PC_CUDA(nullptr, cudaMalloc(&cp->sel.sel, sizeof(int) * 8));
     cp->sel.cub_temp_bytes = select_cub_temp_bytes(cp->cand_cap);
     PC_CUDA(nullptr, cudaMalloc(&cp->sel.cub_temp, cp->sel.cub_temp_bytes));

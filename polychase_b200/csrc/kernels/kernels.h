@@ -42,17 +42,17 @@ void launch_nms_candidates(const float* eig, int eig_pitch, int w, int h, Detect
 // ---- K6/K7: greedy min-distance suppression + ordering (select.cu) --------------------
 struct SelectWorkspace {
     unsigned long long* accepted;      // cap entries
-    unsigned long long* sorted;        // cap entries
+    unsigned long long* sorted;        // sorted_cap = next_pow2(cap) entries (sort output / bitonic spill)
     unsigned long long* strong;        // cap entries: the strongest candidates (max_corners > 0 path)
-    unsigned long long* topk;          // topk_cap entries: the max_corners strongest kept keys
     int* accepted_count;               // device int
     int* round_counters;               // 2 * kMaxGreedyRounds ints
     int* remaining;                    // device int: undecided candidates left (0 = converged)
-    int* hist;                         // 4096 ints
-    int* sel;                          // small device scratch: [0] strong threshold (top 16 bits), [1] strong count
+    int* hist;                         // 4096 ints: 12-bit value histogram of all candidates (written by K5)
+    int* kept_hist;                    // 65536 ints: 16-bit value histogram of kept keys; zero between frames
+    int* sel;                          // small device scratch: [1] strong count
     void* cub_temp; size_t cub_temp_bytes;
     int cap;
-    int topk_cap;
+    int sorted_cap;
 };
 constexpr int kMaxGreedyRounds = 2048;
 size_t select_cub_temp_bytes(int cap);

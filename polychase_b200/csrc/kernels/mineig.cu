@@ -17,113 +17,188 @@
 // running double accumulator carried down each column from row 0; its rounding history
 // changes ~2 pixels per million by a few ulp.  This kernel forms each 3x3 sum
 // independently (the correctly rounded value).
+//
+// Layout (HBM-streaming, no shared memory): one warp owns a 120-column x 32-row output tile and
+// marches down it.  Each lane holds 4 adjacent columns (one aligned 32-bit gray load per row,
+// one aligned 16-byte eig store per row); the +-1 column neighbours come from the adjacent
+// lanes by shuffle, the +-1 row neighbours are rolling registers.  Lanes 0 and 31 only feed
+// their neighbours (the 4+4 halo columns of the tile).
+//
+// Rows outside the image: the march simply continues over the REFLECT_101 row indices.  For
+// the one row each side that the box filter needs (cov row -1 := cov row 1, cov row h := cov
+// row h-2) the mirrored rolling window yields the same dx and the negated dy bit for bit, so
+// cov_xx / cov_yy are already right and cov_xy only needs its sign flipped back.  Columns
+// outside the image take the reflected cov value of the neighbouring lane/column explicitly.
 #include "common.cuh"
 #include "kernels.h"
 
 namespace pc {
 
-constexpr int ME_TW = 64, ME_TH = 16;
-constexpr int ME_GW = ME_TW + 4, ME_GH = ME_TH + 4;      // gray region (halo 2)
-constexpr int ME_DW = ME_TW + 2, ME_DH = ME_TH + 2;      // cov region (halo 1)
+constexpr int ME_COLS = 120;     // output columns per warp tile
+constexpr int ME_ROWS = 32;      // output rows per warp tile
+constexpr int ME_WARPS = 4;
 
 __device__ __forceinline__ int cell_of(int x, int y, const DetectGrid& g) {
     return (y / g.block_h) * g.grid_cols + (x / g.block_w);
 }
 
-__global__ void __launch_bounds__(256) min_eig_kernel(const uint8_t* __restrict__ gray, int w, int h, int pitch,
-                                                      float* __restrict__ eig, int eig_pitch, DetectGrid grid,
-                                                      int* __restrict__ cell_max) {
-    __shared__ uint8_t g[ME_GH][ME_GW + 4];
-    __shared__ float rx[ME_GH][ME_DW], rs[ME_GH][ME_DW];
-    __shared__ float cxx[ME_DH][ME_DW], cxy[ME_DH][ME_DW], cyy[ME_DH][ME_DW];
-    __shared__ int red[8];
+__device__ __forceinline__ uint32_t load_gray4(const uint8_t* __restrict__ gray, int w, int h, int pitch, int x,
+                                               int gy_logical, bool fast) {
+    const uint8_t* row = gray + (size_t)reflect101(gy_logical, h) * pitch;
+    if (fast) return __ldg(reinterpret_cast<const uint32_t*>(row + x));
+    return (uint32_t)row[reflect101(x, w)] | ((uint32_t)row[reflect101(x + 1, w)] << 8) |
+           ((uint32_t)row[reflect101(x + 2, w)] << 16) | ((uint32_t)row[reflect101(x + 3, w)] << 24);
+}
 
-    const int tid = threadIdx.x;
-    const int x0 = blockIdx.x * ME_TW, y0 = blockIdx.y * ME_TH;   // tile origin (output coords)
+__global__ void __launch_bounds__(ME_WARPS * 32) min_eig_kernel(const uint8_t* __restrict__ gray, int w, int h,
+                                                                int pitch, float* __restrict__ eig, int eig_pitch,
+                                                                DetectGrid grid, int* __restrict__ cell_max,
+                                                                int tiles_x, int tiles_y) {
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int tile = blockIdx.x * ME_WARPS + (threadIdx.x >> 5);
+    if (tile >= tiles_x * tiles_y) return;
+    const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+    const int xb = tx * ME_COLS - 4 + 4 * lane;          // this lane's columns xb .. xb+3 (xb % 4 == 0)
+    const int y0 = ty * ME_ROWS;
+    const int y_end = min(y0 + ME_ROWS, h);
     const float s = (float)(1.0 / (4.0 * 3.0 * 255.0));
     const float s2 = 2.0f * s;
     const int wvec = (w / 32) * 32;
+    const bool fast = xb >= 0 && xb + 3 < w;
+    const bool live = xb + 3 >= -1 && xb <= w;             // lanes whose columns can matter at all
+    const bool out_lane = lane >= 1 && lane <= 30 && xb < w;
+    const int jr = (w - 1) - xb;                            // position of the last image column in this lane
 
-    // gray region [x0-2, x0+TW+2) x [y0-2, y0+TH+2), reflected at the image borders
-    for (int idx = tid; idx < ME_GH * ME_GW; idx += 256) {
-        const int r = idx / ME_GW, c = idx - r * ME_GW;
-        const int gy = reflect101(y0 - 2 + r, h), gx = reflect101(x0 - 2 + c, w);
-        g[r][c] = gray[(size_t)gy * pitch + gx];
-    }
-    __syncthreads();
-    // horizontal pass on every region row, for columns x0-1 .. x0+TW
-    for (int idx = tid; idx < ME_GH * ME_DW; idx += 256) {
-        const int r = idx / ME_DW, c = idx - r * ME_DW;             // c <-> global x = x0-1+c
-        const float pm = (float)g[r][c], pc_ = (float)g[r][c + 1], pp = (float)g[r][c + 2];
-        rx[r][c] = __fsub_rn(pp, pm);
-        const int gx = x0 - 1 + c;
-        rs[r][c] = (gx < wvec) ? __fmaf_rn(pp, s, __fmaf_rn(pc_, s2, __fmul_rn(pm, s)))
-                               : __fadd_rn(__fadd_rn(__fmul_rn(pm, s), __fmul_rn(pc_, s2)), __fmul_rn(pp, s));
-    }
-    __syncthreads();
-    // vertical pass + covariance products on [x0-1, x0+TW] x [y0-1, y0+TH]
-    for (int idx = tid; idx < ME_DH * ME_DW; idx += 256) {
-        const int r = idx / ME_DW, c = idx - r * ME_DW;             // r <-> global y = y0-1+r ; region row r+1
-        const float dx = __fmaf_rn(__fadd_rn(rx[r][c], rx[r + 2][c]), s, __fmul_rn(rx[r + 1][c], s2));
-        const float dy = __fsub_rn(rs[r + 2][c], rs[r][c]);
-        cxx[r][c] = __fmul_rn(dx, dx);
-        cxy[r][c] = __fmul_rn(dx, dy);
-        cyy[r][c] = __fmul_rn(dy, dy);
-    }
-    __syncthreads();
-    // cov outside the image is the reflection of cov inside (not cov of reflected gray)
-    auto lc = [&](int gx) { return reflect101(gx, w) - (x0 - 1); };  // local column of global x
-    auto lr = [&](int gy) { return reflect101(gy, h) - (y0 - 1); };
+    // grid cell bookkeeping: the common case is one cell column per warp tile
+    int cx[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) cx[j] = min(max(xb + j, 0), w - 1) / grid.block_w;
+    const int cx_ref = __shfl_sync(FULL, cx[0], 1);
+    const bool my_uniform = !out_lane || (cx[0] == cx_ref && cx[3] == cx_ref);
+    const bool uniform_x = __all_sync(FULL, my_uniform);
+    int run_max = (int)0x80000000, run_cy = y0 / grid.block_h;
 
-    const int col = tid & (ME_TW - 1), rg = tid / ME_TW;            // 4 row groups of 4 rows
-    const int gx = x0 + col;
-    int local_max = 0x80000000;
-    if (gx < w) {
-        const int cm = lc(gx - 1), cc = col + 1, cp = lc(gx + 1);
-        double Rxx[3], Rxy[3], Ryy[3];
-        auto rowsum = [&](int gy, double& oxx, double& oxy, double& oyy) {
-            const int r = lr(gy);
-            oxx = __dadd_rn(__dadd_rn((double)cxx[r][cm], (double)cxx[r][cc]), (double)cxx[r][cp]);
-            oxy = __dadd_rn(__dadd_rn((double)cxy[r][cm], (double)cxy[r][cc]), (double)cxy[r][cp]);
-            oyy = __dadd_rn(__dadd_rn((double)cyy[r][cm], (double)cyy[r][cc]), (double)cyy[r][cp]);
-        };
-        const int gy0 = y0 + rg * 4;
-        if (gy0 < h) {
-            rowsum(gy0 - 1, Rxx[0], Rxy[0], Ryy[0]);
-            rowsum(gy0, Rxx[1], Rxy[1], Ryy[1]);
+    float rx[3][4], rsm[3][4];                 // rolling horizontal passes (rows k-2, k-1, k)
+    double Rp[3][4], T[3][4];                  // rowsum of the previous cov row, and prev-prev + prev
+#pragma unroll
+    for (int c = 0; c < 3; c++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) { Rp[c][j] = 0.0; T[c][j] = 0.0; }
+#pragma unroll
+    for (int r = 0; r < 3; r++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) { rx[r][j] = 0.f; rsm[r][j] = 0.f; }
+
+    uint32_t word = live ? load_gray4(gray, w, h, pitch, xb, y0 - 2, fast) : 0u;
+    const int steps = (y_end - y0) + 4;
+    for (int k = 0; k < steps; k++) {
+        // prefetch the next gray row while this one is processed
+        uint32_t next_word = 0u;
+        if (live && k + 1 < steps) next_word = load_gray4(gray, w, h, pitch, xb, y0 - 1 + k, fast);
+
+        // ---- horizontal pass on gray row (logical) y0 - 2 + k ---------------------------------
+        const uint32_t wl = __shfl_up_sync(FULL, word, 1), wr = __shfl_down_sync(FULL, word, 1);
+        float p[6];
+        p[0] = (float)(wl >> 24);
+        p[1] = (float)(word & 255u); p[2] = (float)((word >> 8) & 255u);
+        p[3] = (float)((word >> 16) & 255u); p[4] = (float)(word >> 24);
+        p[5] = (float)(wr & 255u);
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            rx[0][j] = rx[1][j]; rx[1][j] = rx[2][j];
+            rsm[0][j] = rsm[1][j]; rsm[1][j] = rsm[2][j];
+            const float pm = p[j], pc_ = p[j + 1], pp = p[j + 2];
+            rx[2][j] = __fsub_rn(pp, pm);
+            rsm[2][j] = (xb + j < wvec) ? __fmaf_rn(pp, s, __fmaf_rn(pc_, s2, __fmul_rn(pm, s)))
+                                        : __fadd_rn(__fadd_rn(__fmul_rn(pm, s), __fmul_rn(pc_, s2)), __fmul_rn(pp, s));
+        }
+        word = next_word;
+        if (k < 2) continue;
+
+        // ---- cov row (logical) cy = y0 - 3 + k ------------------------------------------------
+        const int cy = y0 - 3 + k;
+        const bool flip = cy < 0 || cy >= h;                // mirrored window: dy came out negated
+        float c[3][4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const float dx = __fmaf_rn(__fadd_rn(rx[0][j], rx[2][j]), s, __fmul_rn(rx[1][j], s2));
+            const float dy = __fsub_rn(rsm[2][j], rsm[0][j]);
+            c[0][j] = __fmul_rn(dx, dx);
+            const float xy = __fmul_rn(dx, dy);
+            c[1][j] = flip ? -xy : xy;
+            c[2][j] = __fmul_rn(dy, dy);
+        }
+        // ---- 3-tap horizontal sums in double, REFLECT_101 of cov at the image's side borders --
+        double R[3][4];
+#pragma unroll
+        for (int ch = 0; ch < 3; ch++) {
+            double d[6];
+            d[0] = (double)__shfl_up_sync(FULL, c[ch][3], 1);
+            d[5] = (double)__shfl_down_sync(FULL, c[ch][0], 1);
+#pragma unroll
+            for (int j = 0; j < 4; j++) d[j + 1] = (double)c[ch][j];
+            if (xb == 0) d[0] = d[2];                       // cov[-1] := cov[1]
+            if ((unsigned)jr < 4u) {                        // cov[w] := cov[w-2]
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+                    if (j == jr) d[j + 2] = d[j];
+            }
+#pragma unroll
+            for (int j = 0; j < 4; j++) R[ch][j] = __dadd_rn(__dadd_rn(d[j], d[j + 1]), d[j + 2]);
+        }
+        // ---- 3-tap vertical sums, eigenvalue, store (output row y = cy - 1) --------------------
+        const int y = cy - 1;
+        if (k >= 4 && y < h) {
+            float v[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const float sxx = (float)__dadd_rn(T[0][j], R[0][j]);
+                const float sxy = (float)__dadd_rn(T[1][j], R[1][j]);
+                const float syy = (float)__dadd_rn(T[2][j], R[2][j]);
+                const float a = __fmul_rn(sxx, 0.5f), b = sxy, cc = __fmul_rn(syy, 0.5f);
+                const float t = __fsub_rn(a, cc);
+                v[j] = __fsub_rn(__fadd_rn(a, cc), __fsqrt_rn(__fadd_rn(__fmul_rn(t, t), __fmul_rn(b, b))));
+            }
+            const int cyc = y / grid.block_h;
+            if (cyc != run_cy) {                            // warp-uniform: the tile crossed a cell row
+                if (uniform_x) {
+                    const int m = __reduce_max_sync(FULL, run_max);
+                    if (lane == 0 && m != (int)0x80000000) atomicMax(&cell_max[run_cy * grid.grid_cols + cx_ref], m);
+                }
+                run_max = (int)0x80000000;
+                run_cy = cyc;
+            }
+            if (out_lane) {
+                float* dst = eig + (size_t)y * eig_pitch + xb;
+                if (xb + 3 < w) {
+                    *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; j++)
+                        if (xb + j < w) dst[j] = v[j];
+                }
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    if (xb + j < w) {
+                        const int ov = float_to_ordered_int(v[j]);
+                        if (uniform_x) run_max = max(run_max, ov);
+                        else atomicMax(&cell_max[cyc * grid.grid_cols + cx[j]], ov);
+                    }
+                }
+            }
         }
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const int gy = gy0 + k;
-            if (gy >= h) break;
-            rowsum(gy + 1, Rxx[2], Rxy[2], Ryy[2]);
-            const float sxx = (float)__dadd_rn(__dadd_rn(Rxx[0], Rxx[1]), Rxx[2]);
-            const float sxy = (float)__dadd_rn(__dadd_rn(Rxy[0], Rxy[1]), Rxy[2]);
-            const float syy = (float)__dadd_rn(__dadd_rn(Ryy[0], Ryy[1]), Ryy[2]);
-            const float a = __fmul_rn(sxx, 0.5f), b = sxy, c = __fmul_rn(syy, 0.5f);
-            const float t = __fsub_rn(a, c);
-            const float v = __fsub_rn(__fadd_rn(a, c), __fsqrt_rn(__fadd_rn(__fmul_rn(t, t), __fmul_rn(b, b))));
-            eig[(size_t)gy * eig_pitch + gx] = v;
-            const int ov = float_to_ordered_int(v);
-            const int cell = cell_of(gx, gy, grid);
-            // tiles that straddle a cell boundary fall back to per-pixel atomics below
-            if (cell == cell_of(x0, y0, grid)) local_max = max(local_max, ov);
-            else atomicMax(&cell_max[cell], ov);
-            Rxx[0] = Rxx[1]; Rxx[1] = Rxx[2];
-            Rxy[0] = Rxy[1]; Rxy[1] = Rxy[2];
-            Ryy[0] = Ryy[1]; Ryy[1] = Ryy[2];
-        }
+        for (int ch = 0; ch < 3; ch++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                T[ch][j] = __dadd_rn(Rp[ch][j], R[ch][j]);
+                Rp[ch][j] = R[ch][j];
+            }
     }
-    // block max of the pixels that share the tile origin's cell -> one atomic
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) local_max = max(local_max, __shfl_xor_sync(0xffffffffu, local_max, o));
-    if ((tid & 31) == 0) red[tid >> 5] = local_max;
-    __syncthreads();
-    if (tid == 0) {
-        int m = red[0];
-#pragma unroll
-        for (int k = 1; k < 8; k++) m = max(m, red[k]);
-        if (m != (int)0x80000000) atomicMax(&cell_max[cell_of(x0, y0, grid)], m);
+    if (uniform_x) {
+        const int m = __reduce_max_sync(FULL, run_max);
+        if (lane == 0 && m != (int)0x80000000) atomicMax(&cell_max[run_cy * grid.grid_cols + cx_ref], m);
     }
 }
 
@@ -136,65 +211,138 @@ __global__ void init_cell_max_kernel(int* cell_max, int n, int* counters, int n_
 void launch_min_eig(Image8 gray, float* eig, int eig_pitch, DetectGrid g, int* cell_max, cudaStream_t s) {
     const int ncell = g.grid_rows * g.grid_cols;
     init_cell_max_kernel<<<(ncell + 255) / 256, 256, 0, s>>>(cell_max, ncell, nullptr, 0);
-    dim3 grid((gray.w + ME_TW - 1) / ME_TW, (gray.h + ME_TH - 1) / ME_TH);
-    min_eig_kernel<<<grid, 256, 0, s>>>(gray.data, gray.w, gray.h, gray.pitch, eig, eig_pitch, g, cell_max);
+    const int tiles_x = (gray.w + ME_COLS - 1) / ME_COLS, tiles_y = (gray.h + ME_ROWS - 1) / ME_ROWS;
+    const int blocks = (tiles_x * tiles_y + ME_WARPS - 1) / ME_WARPS;
+    min_eig_kernel<<<blocks, ME_WARPS * 32, 0, s>>>(gray.data, gray.w, gray.h, gray.pitch, eig, eig_pitch, g, cell_max,
+                                                    tiles_x, tiles_y);
 }
 
 // ---- K5: threshold (per cell), 3x3 NMS, candidate list + state map ---------------------
 // cv::threshold(THRESH_TOZERO, maxVal*quality): thresh is the double product rounded to
 // float; value kept iff value > thresh (gftt.cc:61-65).  A pixel is a candidate iff it is
-// interior, its thresholded value is non-zero and equals the 3x3 max (gftt.cc:70-86).
-__global__ void __launch_bounds__(256) nms_candidates_kernel(const float* __restrict__ eig, int eig_pitch, int w,
-                                                             int h, DetectGrid grid,
-                                                             const int* __restrict__ cell_max, double quality,
-                                                             uint8_t* __restrict__ state, int state_pitch,
-                                                             unsigned long long* __restrict__ cand, int cand_cap,
-                                                             int* __restrict__ cand_count,
-                                                             int* __restrict__ value_hist) {
-    const int x = blockIdx.x * 64 + (threadIdx.x & 63);
-    const int y = blockIdx.y * 4 + (threadIdx.x >> 6);
-    bool is_cand = false;
-    float v = 0.f;
-    if (x < w && y < h) {
-        auto thr_at = [&](int cx, int cy) {
-            const float m = ordered_int_to_float(__ldg(&cell_max[cell_of(cx, cy, grid)]));
-            return (float)((double)m * quality);
-        };
-        auto tz = [&](float val, float thr) { return val > thr ? val : 0.f; };
-        if (x >= 1 && y >= 1 && x < w - 1 && y < h - 1) {
-            const float thr_c = thr_at(x, y);
-            v = tz(eig[(size_t)y * eig_pitch + x], thr_c);
-            if (v != 0.f) {
-                const int bx = x % grid.block_w, by = y % grid.block_h;
-                const bool inner_cell = bx > 0 && bx < grid.block_w - 1 && by > 0 && by < grid.block_h - 1;
-                is_cand = true;
+// interior, its thresholded value is non-zero and equals the 3x3 max of the thresholded map
+// (gftt.cc:70-86).
+//
+// One warp owns a 128-column strip of NMS_ROWS rows and marches down it: per row one 16-byte
+// eig load per lane (4 columns), thresholded on load with the threshold of the pixel's own
+// cell (table in shared memory), +-1 column from the neighbour lanes (strip-edge lanes load
+// the one extra column), rows in rolling registers.  Writes the u8 state map (4 bytes per lane
+// per row) and appends candidates (warp-aggregated).
+constexpr int NMS_ROWS = 16;
+constexpr int NMS_WARPS = 4;
+constexpr int NMS_MAX_CELLS = 4096;    // = pc_ctx::cell_cap
+
+__global__ void __launch_bounds__(NMS_WARPS * 32) nms_candidates_kernel(
+    const float* __restrict__ eig, int eig_pitch, int w, int h, DetectGrid grid, const int* __restrict__ cell_max,
+    double quality, uint8_t* __restrict__ state, int state_pitch, unsigned long long* __restrict__ cand, int cand_cap,
+    int* __restrict__ cand_count, int* __restrict__ value_hist, int tiles_x, int tiles_y) {
+    const unsigned FULL = 0xffffffffu;
+    __shared__ float thr_tab[NMS_MAX_CELLS];
+    const int ncell = grid.grid_rows * grid.grid_cols;
+    for (int i = threadIdx.x; i < ncell; i += blockDim.x)
+        thr_tab[i] = (float)((double)ordered_int_to_float(__ldg(&cell_max[i])) * quality);
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int tile = blockIdx.x * NMS_WARPS + (threadIdx.x >> 5);
+    if (tile >= tiles_x * tiles_y) return;
+    const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+    const int xb = tx * 128 + 4 * lane;
+    const int y0 = ty * NMS_ROWS, y_end = min(y0 + NMS_ROWS, h);
+    const bool live = xb < w;
+    int cxj[6];                                   // cell column of x = xb-1 .. xb+4
 #pragma unroll
-                for (int dy = -1; dy <= 1; dy++)
+    for (int j = 0; j < 6; j++) cxj[j] = min(max(xb - 1 + j, 0), w - 1) / grid.block_w;
+
+    // raw values of one row: this lane's 4 columns + (strip-edge lanes only) the column beside them
+    struct RawRow { float4 v; float edge; };
+    auto fetch = [&](int y) {
+        RawRow r;
+        r.v = make_float4(0.f, 0.f, 0.f, 0.f);
+        r.edge = 0.f;
+        if ((unsigned)y >= (unsigned)h || !live) return r;
+        const float* row = eig + (size_t)y * eig_pitch;
+        if (xb + 3 < w) r.v = *reinterpret_cast<const float4*>(row + xb);
+        else {
+            r.v.x = row[xb];
+            if (xb + 1 < w) r.v.y = row[xb + 1];
+            if (xb + 2 < w) r.v.z = row[xb + 2];
+        }
+        if (lane == 0 && xb >= 1) r.edge = row[xb - 1];
+        if (lane == 31 && xb + 4 < w) r.edge = row[xb + 4];
+        return r;
+    };
+    // thresholded values for columns xb-1 .. xb+4 (0 outside the image: never a max, and border
+    // pixels are never candidates)
+    auto finish = [&](int y, const RawRow& r, float (&t)[6]) {
 #pragma unroll
-                    for (int dx = -1; dx <= 1; dx++) {
-                        if (dx == 0 && dy == 0) continue;
-                        const float thr = inner_cell ? thr_c : thr_at(x + dx, y + dy);
-                        const float nv = tz(eig[(size_t)(y + dy) * eig_pitch + x + dx], thr);
-                        if (nv > v) is_cand = false;
-                    }
+        for (int j = 0; j < 6; j++) t[j] = 0.f;
+        if ((unsigned)y >= (unsigned)h) return;   // warp-uniform
+        const int crow = (y / grid.block_h) * grid.grid_cols;
+        const float raw[4] = {r.v.x, r.v.y, r.v.z, r.v.w};
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const float th = thr_tab[crow + cxj[j + 1]];
+            t[j + 1] = (live && xb + j < w && raw[j] > th) ? raw[j] : 0.f;
+        }
+        float left = __shfl_up_sync(FULL, t[4], 1), right = __shfl_down_sync(FULL, t[1], 1);
+        if (lane == 0) left = (live && xb >= 1 && r.edge > thr_tab[crow + cxj[0]]) ? r.edge : 0.f;
+        if (lane == 31) right = (xb + 4 < w && r.edge > thr_tab[crow + cxj[5]]) ? r.edge : 0.f;
+        t[0] = left;
+        t[5] = right;
+    };
+
+    float a[6], b[6], c[6];                       // rows y-1, y, y+1
+    finish(y0 - 1, fetch(y0 - 1), a);
+    finish(y0, fetch(y0), b);
+    RawRow ahead = fetch(y0 + 1);
+    for (int y = y0; y < y_end; y++) {
+        const RawRow cur = ahead;
+        ahead = fetch(y + 2);                     // in flight while this row is processed
+        finish(y + 1, cur, c);
+        uint32_t bits = 0;
+        bool is_c[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const float vmid = b[j + 1];
+            float m = fmaxf(fmaxf(a[j], a[j + 1]), a[j + 2]);
+            m = fmaxf(m, fmaxf(b[j], b[j + 2]));
+            m = fmaxf(m, fmaxf(fmaxf(c[j], c[j + 1]), c[j + 2]));
+            const int x = xb + j;
+            is_c[j] = vmid != 0.f && vmid >= m && x >= 1 && x < w - 1 && y >= 1 && y < h - 1;
+            bits |= is_c[j] ? (1u << (8 * j)) : 0u;
+        }
+        if (live) {
+            uint8_t* sp = state + (size_t)y * state_pitch + xb;
+            if (xb + 3 < w) *reinterpret_cast<uint32_t*>(sp) = bits;
+            else
+                for (int j = 0; j < 4 && xb + j < w; j++) sp[j] = (bits >> (8 * j)) & 1u;
+        }
+        // warp-aggregated append (order inside the list is irrelevant: keys are sorted later)
+        const int mine = (int)is_c[0] + (int)is_c[1] + (int)is_c[2] + (int)is_c[3];
+        if (__any_sync(FULL, mine > 0)) {
+            int incl = mine;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int n = __shfl_up_sync(FULL, incl, o);
+                if (lane >= o) incl += n;
+            }
+            const int total = __shfl_sync(FULL, incl, 31);
+            int base = 0;
+            if (lane == 31) base = atomicAdd(cand_count, total);
+            base = __shfl_sync(FULL, base, 31);
+            int slot = base + incl - mine;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                if (is_c[j]) {
+                    const uint32_t ov = float_to_ordered_uint(b[j + 1]);
+                    if (slot < cand_cap) cand[slot] = ((unsigned long long)ov << 32) | (unsigned)(y * w + xb + j);
+                    slot++;
+                    atomicAdd(&value_hist[ov >> 20], 1);
+                }
             }
         }
-        state[(size_t)y * state_pitch + x] = is_cand ? 1 : 0;
-    }
-    // warp-aggregated append
-    const unsigned mask = __ballot_sync(0xffffffffu, is_cand);
-    if (mask) {
-        const int lane = threadIdx.x & 31;
-        const int leader = __ffs(mask) - 1;
-        int base = 0;
-        if (lane == leader) base = atomicAdd(cand_count, __popc(mask));
-        base = __shfl_sync(0xffffffffu, base, leader);
-        if (is_cand) {
-            const int slot = base + __popc(mask & ((1u << lane) - 1));
-            const uint32_t ov = float_to_ordered_uint(v);
-            if (slot < cand_cap) cand[slot] = ((unsigned long long)ov << 32) | (unsigned)(y * w + x);
-            atomicAdd(&value_hist[ov >> 20], 1);
-        }
+#pragma unroll
+        for (int j = 0; j < 6; j++) { a[j] = b[j]; b[j] = c[j]; }
     }
 }
 
@@ -203,9 +351,11 @@ void launch_nms_candidates(const float* eig, int eig_pitch, int w, int h, Detect
                            int cand_cap, int* cand_count, int* value_hist, cudaStream_t s) {
     cudaMemsetAsync(cand_count, 0, sizeof(int), s);
     cudaMemsetAsync(value_hist, 0, sizeof(int) * 4096, s);
-    dim3 grid((w + 63) / 64, (h + 3) / 4);
-    nms_candidates_kernel<<<grid, 256, 0, s>>>(eig, eig_pitch, w, h, g, cell_max, quality_level, state, state_pitch,
-                                               cand, cand_cap, cand_count, value_hist);
+    const int tiles_x = (w + 127) / 128, tiles_y = (h + NMS_ROWS - 1) / NMS_ROWS;
+    const int blocks = (tiles_x * tiles_y + NMS_WARPS - 1) / NMS_WARPS;
+    nms_candidates_kernel<<<blocks, NMS_WARPS * 32, 0, s>>>(eig, eig_pitch, w, h, g, cell_max, quality_level, state,
+                                                            state_pitch, cand, cand_cap, cand_count, value_hist,
+                                                            tiles_x, tiles_y);
 }
 
 }  // namespace pc

@@ -11,15 +11,17 @@
 // formulation: a candidate becomes REJECTED as soon as a stronger in-disc candidate is
 // KEPT, and KEPT once every stronger in-disc candidate is decided and none is kept.
 // A persistent cooperative kernel iterates that to its fixed point (grid-wide barrier per
-// round, no host round trips).
+// round, no host round trips); the dependency depth measured on 4K frames is <= 10 rounds.
 //
 // With max_corners > 0 the reference stops after max_corners kept corners (gftt.cc:160-162),
 // i.e. it returns a prefix of the unlimited result.  Because decisions only depend on stronger
 // candidates, the fixed point is first run on the strongest ~4*max_corners candidates (a value
 // threshold from a 12-bit histogram); only if that yields fewer than max_corners kept corners
-// does a second pass process everything.  The max_corners strongest kept keys are then
-// extracted exactly with a 4-pass radix select and sorted (64-bit radix sort on
-// (value, address) descending).  With max_corners == 0 every kept key is sorted.
+// does a second pass process everything.  Kept keys are counted into a 16-bit-bin histogram
+// of their value as they are accepted; one CTA then finds the bin that holds the
+// max_corners-th strongest key, gathers the keys at or above it into shared memory, sorts them
+// (bitonic, (value, address) descending) and writes the first max_corners as keypoints.
+// With max_corners == 0 every kept key is sorted (CUB radix sort).
 #include <cooperative_groups.h>
 #include <cub/device/device_radix_sort.cuh>
 
@@ -32,12 +34,83 @@ namespace pc {
 
 enum : uint8_t { ST_NONE = 0, ST_UNDECIDED = 1, ST_KEPT = 2, ST_REJECTED = 3 };
 
+__device__ __forceinline__ unsigned long long key_at(const float* __restrict__ eig, int eig_pitch, int w, int x,
+                                                     int y) {
+    return ((unsigned long long)float_to_ordered_uint(eig[(size_t)y * eig_pitch + x]) << 32) | (unsigned)(y * w + x);
+}
+
+// Decision for one undecided candidate from the current state map: 0 = still blocked by an
+// undecided stronger neighbour, ST_KEPT or ST_REJECTED.  R <= 4 takes the word-wide path: the
+// 9 rows x 3 aligned words that cover the disc's bounding box are loaded up front
+// (independent L2 loads), then only the non-zero state bytes are looked at.
+__device__ __forceinline__ int decide(unsigned long long key, int x, int y, const float* __restrict__ eig,
+                                      int eig_pitch, const uint8_t* state, int state_pitch, int w, int h, int R,
+                                      double md2) {
+    bool blocked = false;
+    if (R <= 4) {
+        const int xl = x - 4, wx0 = xl & ~3;                 // may be negative: masked below
+        uint32_t wd[9][3];
+#pragma unroll
+        for (int r = 0; r < 9; r++) {
+            const int ny = y - 4 + r;
+            const bool row_ok = (unsigned)ny < (unsigned)h;
+            const uint8_t* row = state + (size_t)(row_ok ? ny : y) * state_pitch;
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                const int wx = wx0 + 4 * k;
+                // state_pitch is a multiple of 128 >= w: an aligned word that starts inside the
+                // pitch is readable; bytes at x >= w are skipped below
+                wd[r][k] = (row_ok && wx >= 0 && wx < state_pitch) ? __ldcg(reinterpret_cast<const uint32_t*>(row + wx)) : 0u;
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < 9; r++) {
+            const int dy = r - 4;
+            if (dy < -R || dy > R) continue;
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                uint32_t v = wd[r][k];
+                while (v) {
+                    const int b = (__ffs(v) - 1) >> 3;
+                    const uint32_t ns = (v >> (8 * b)) & 0xffu;
+                    v &= ~(0xffu << (8 * b));
+                    const int nx = wx0 + 4 * k + b, dx = nx - x;
+                    if (dx < -R || dx > R || (dx == 0 && dy == 0) || nx < 0 || nx >= w) continue;
+                    if ((double)(dx * dx + dy * dy) >= md2) continue;
+                    if (ns != ST_UNDECIDED && ns != ST_KEPT) continue;
+                    if (key_at(eig, eig_pitch, w, nx, y + dy) > key) {
+                        if (ns == ST_KEPT) return ST_REJECTED;
+                        blocked = true;
+                    }
+                }
+            }
+        }
+    } else {
+        for (int dy = -R; dy <= R; dy++) {
+            const int ny = y + dy;
+            if (ny < 0 || ny >= h) continue;
+            for (int dx = -R; dx <= R; dx++) {
+                const int nx = x + dx;
+                if (nx < 0 || nx >= w || (dx == 0 && dy == 0)) continue;
+                if ((double)(dx * dx + dy * dy) >= md2) continue;
+                const uint8_t ns = __ldcg(state + (size_t)ny * state_pitch + nx);
+                if (ns != ST_UNDECIDED && ns != ST_KEPT) continue;
+                if (key_at(eig, eig_pitch, w, nx, ny) > key) {
+                    if (ns == ST_KEPT) return ST_REJECTED;
+                    blocked = true;
+                }
+            }
+        }
+    }
+    return blocked ? 0 : ST_KEPT;
+}
+
 // list/count: candidates to decide in this launch.  If enough_at > 0 and that many corners are
 // already kept, the launch is a no-op (second, full pass of the max_corners path).
 __global__ void __launch_bounds__(256) greedy_suppress_kernel(
     const unsigned long long* __restrict__ cand, const int* __restrict__ cand_count, int cand_cap,
     const float* __restrict__ eig, int eig_pitch, uint8_t* state, int state_pitch, int w, int h, int R,
-    double md2, unsigned long long* __restrict__ accepted, int* accepted_count, int* round_counters,
+    double md2, unsigned long long* __restrict__ accepted, int* accepted_count, int* kept_hist, int* round_counters,
     int* remaining, int enough_at) {
     cg::grid_group grid = cg::this_grid();
     __shared__ int block_undecided;
@@ -60,30 +133,13 @@ __global__ void __launch_bounds__(256) greedy_suppress_kernel(
             const int y = addr / w, x = addr - y * w;
             uint8_t* sp = state + (size_t)y * state_pitch + x;
             if (__ldcg(sp) != ST_UNDECIDED) continue;
-            bool blocked = false, rejected = false;
-            for (int dy = -R; dy <= R && !rejected; dy++) {
-                const int ny = y + dy;
-                if (ny < 0 || ny >= h) continue;
-                for (int dx = -R; dx <= R; dx++) {
-                    const int nx = x + dx;
-                    if (nx < 0 || nx >= w || (dx == 0 && dy == 0)) continue;
-                    if ((double)(dx * dx + dy * dy) >= md2) continue;
-                    const uint8_t ns = __ldcg(state + (size_t)ny * state_pitch + nx);
-                    if (ns != ST_UNDECIDED && ns != ST_KEPT) continue;
-                    const unsigned long long nkey =
-                        ((unsigned long long)float_to_ordered_uint(eig[(size_t)ny * eig_pitch + nx]) << 32) |
-                        (unsigned)(ny * w + nx);
-                    if (nkey > key) {
-                        if (ns == ST_KEPT) { rejected = true; break; }
-                        blocked = true;
-                    }
-                }
-            }
-            if (rejected) {
+            const int d = decide(key, x, y, eig, eig_pitch, state, state_pitch, w, h, R, md2);
+            if (d == ST_REJECTED) {
                 *sp = ST_REJECTED;
-            } else if (!blocked) {
+            } else if (d == ST_KEPT) {
                 *sp = ST_KEPT;
                 accepted[atomicAdd(accepted_count, 1)] = key;
+                if (kept_hist) atomicAdd(&kept_hist[(unsigned)(key >> 48)], 1);
             } else {
                 undecided++;
             }
@@ -100,49 +156,62 @@ __global__ void __launch_bounds__(256) greedy_suppress_kernel(
 
 __global__ void accept_all_kernel(const unsigned long long* __restrict__ cand, const int* __restrict__ cand_count,
                                   int cand_cap, unsigned long long* __restrict__ accepted, int* accepted_count,
-                                  int* remaining) {
+                                  int* kept_hist, int* remaining) {
     const int n = min(*cand_count, cand_cap);
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) accepted[i] = cand[i];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const unsigned long long key = cand[i];
+        accepted[i] = key;
+        if (kept_hist) atomicAdd(&kept_hist[(unsigned)(key >> 48)], 1);
+    }
     if (blockIdx.x == 0 && threadIdx.x == 0) { *accepted_count = n; *remaining = 0; }
 }
 
-// sel[0] <- the largest 12-bit value bin b (ordered value >> 20) such that at least `want`
-// candidates have bin >= b (0 if there are fewer candidates than that): the strong threshold.
-__global__ void __launch_bounds__(1024) strong_threshold_kernel(const int* __restrict__ hist, int want, int* sel) {
-    __shared__ int wsum[32];
-    const int t = threadIdx.x;
-    const int4 hv = __ldcg(reinterpret_cast<const int4*>(hist) + t);      // bins 4t .. 4t+3
-    const int s = hv.x + hv.y + hv.z + hv.w;
-    int v = s;
-    const int lane = t & 31, wid = t >> 5;
+// Block-wide "largest bin b whose suffix count reaches `want`" over a histogram in global memory,
+// PER_THREAD consecutive bins per thread (descending search).  Returns the bin, or 0 if the whole
+// histogram holds fewer than `want`.
+template <int THREADS, int PER_THREAD>
+__device__ __forceinline__ int suffix_threshold_bin(const int* hist, int want, int* s_warp, int* s_bin) {
+    const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+    const int4* hp = reinterpret_cast<const int4*>(hist) + t * (PER_THREAD / 4);
+    int s = 0;
+#pragma unroll
+    for (int q = 0; q < PER_THREAD / 4; q++) {
+        const int4 v = __ldcg(hp + q);
+        s += v.x + v.y + v.z + v.w;
+    }
+    int v = s;                                              // suffix sum inside the warp (lanes >= lane)
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-        const int n = __shfl_down_sync(0xffffffffu, v, o);
-        if (lane + o < 32) v += n;
+        const int nb = __shfl_down_sync(0xffffffffu, v, o);
+        if (lane + o < 32) v += nb;
     }
-    if (lane == 0) wsum[wid] = v;
-    if (t == 0) { sel[0] = 0; sel[1] = 0; }
+    if (lane == 0) s_warp[wid] = v;
+    if (t == 0) *s_bin = 0;
     __syncthreads();
-    int above = 0;                                  // candidates in warps above this one
-    for (int k = wid + 1; k < 32; k++) above += wsum[k];
+    int above = 0;
+    for (int q = wid + 1; q < THREADS / 32; q++) above += s_warp[q];
     const int suf_incl = v + above, suf_excl = suf_incl - s;
-    if (suf_excl < want && want <= suf_incl) {      // the boundary bin is in this thread's range
-        const int h4[4] = {hv.x, hv.y, hv.z, hv.w};
+    if (suf_excl < want && want <= suf_incl) {              // the boundary bin is in this thread's range
         int acc = suf_excl;
-        for (int k = 3; k >= 0; k--) {
-            acc += h4[k];
-            if (acc >= want) { sel[0] = t * 4 + k; break; }
+        for (int k = PER_THREAD - 1; k >= 0; k--) {
+            acc += __ldcg(hist + t * PER_THREAD + k);
+            if (acc >= want) { *s_bin = t * PER_THREAD + k; break; }
         }
     }
+    __syncthreads();
+    return *s_bin;
 }
 
+// Strong candidates: those whose 12-bit value bin is at or above the bin at which the suffix
+// count of the NMS histogram reaches `want` (every block recomputes that bin: 4096 ints).
 __global__ void __launch_bounds__(256) compact_strong_kernel(const unsigned long long* __restrict__ cand,
                                                              const int* __restrict__ cand_count, int cand_cap,
-                                                             const int* __restrict__ sel,
+                                                             const int* hist, int want,
                                                              unsigned long long* __restrict__ strong,
                                                              int* __restrict__ strong_count) {
+    __shared__ int s_warp[8], s_bin;
+    const unsigned thr = (unsigned)suffix_threshold_bin<256, 16>(hist, want, s_warp, &s_bin);
     const int n = min(*cand_count, cand_cap);
-    const unsigned thr = (unsigned)sel[0];
     for (int base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
         const int i = base + threadIdx.x;
         unsigned long long key = 0;
@@ -162,80 +231,84 @@ __global__ void __launch_bounds__(256) compact_strong_kernel(const unsigned long
     }
 }
 
-// Exact selection of the k = min(max_corners, n) largest keys (one CTA): 8 radix passes of 8
-// bits with shared-memory histograms find the k-th largest key, then every key >= it is copied
-// to `out` (zero padded to out_cap so that a fixed-size sort can follow).
-__global__ void __launch_bounds__(1024) topk_select_kernel(const unsigned long long* __restrict__ keys,
-                                                           const int* __restrict__ n_ptr, int max_corners,
-                                                           unsigned long long* __restrict__ out, int out_cap) {
-    __shared__ int h[256];
-    __shared__ int wsum[8];
-    __shared__ unsigned long long s_prefix;
-    __shared__ int s_krem, s_out;
-    const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
-    const int n = *n_ptr;
-    const int k = min(max_corners, n);
-    for (int i = t; i < out_cap; i += 1024) out[i] = 0ull;
-    if (t == 0) { s_prefix = 0ull; s_krem = k; s_out = 0; }
-    __syncthreads();
-    unsigned long long kth = 0ull;
-    if (n > k) {
-        for (int d = 7; d >= 0; d--) {
-            if (t < 256) h[t] = 0;
-            __syncthreads();
-            const unsigned long long prefix = s_prefix;
-            const int shift = 8 * d;
-            for (int i = t; i < n; i += 1024) {
-                const unsigned long long key = keys[i];
-                const bool match = d == 7 ? true : ((key >> (shift + 8)) == (prefix >> (shift + 8)));
-                if (match) atomicAdd(&h[(unsigned)(key >> shift) & 0xffu], 1);
-            }
-            __syncthreads();
-            const int krem = s_krem;
-            int s = 0, v = 0;
-            if (t < 256) {
-                s = h[t];
-                v = s;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const int nb = __shfl_down_sync(0xffffffffu, v, o);
-                    if (lane + o < 32) v += nb;
-                }
-                if (lane == 0) wsum[wid] = v;
-            }
-            __syncthreads();
-            if (t < 256) {
-                int above = 0;
-                for (int q = wid + 1; q < 8; q++) above += wsum[q];
-                const int suf_incl = v + above, suf_excl = suf_incl - s;    // bins >= t / bins > t
-                if (suf_excl < krem && krem <= suf_incl) {
-                    s_prefix = prefix | ((unsigned long long)t << shift);
-                    s_krem = krem - suf_excl;                              // rank inside the chosen bin
-                }
+// ---- final selection: top max_corners kept keys, sorted, as keypoints (one CTA) --------------
+constexpr int SORT_THREADS = 1024;
+constexpr int SORT_SMEM_KEYS = 16384;                       // 128 KB of dynamic shared memory
+
+__device__ __forceinline__ void bitonic_sort_desc(unsigned long long* a, int P) {
+    for (int size = 2; size <= P; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int i = threadIdx.x; i < (P >> 1); i += SORT_THREADS) {
+                const int pos = 2 * i - (i & (stride - 1));
+                const unsigned long long u = a[pos], v = a[pos + stride];
+                const bool desc = (pos & size) == 0;
+                if (desc ? (u < v) : (u > v)) { a[pos] = v; a[pos + stride] = u; }
             }
             __syncthreads();
         }
-        kth = s_prefix;
     }
-    for (int base = 0; base < n; base += 1024) {
+}
+
+__global__ void __launch_bounds__(SORT_THREADS) select_sort_emit_kernel(
+    const unsigned long long* __restrict__ accepted, const int* __restrict__ accepted_count, int* kept_hist,
+    int max_corners, unsigned long long* __restrict__ spill, int spill_cap, int w, float* __restrict__ kps,
+    int kps_cap, int* __restrict__ kps_count) {
+    extern __shared__ __align__(16) unsigned long long s_keys[];
+    __shared__ int s_warp[SORT_THREADS / 32], s_bin, s_fill;
+    const int t = threadIdx.x;
+    const int n = *accepted_count;
+    const int k = min(min(max_corners, n), kps_cap);
+    // 1. the 16-bit value bin that holds the k-th strongest kept key; the histogram is handed
+    //    back zeroed for the next frame
+    const unsigned thr = (unsigned)suffix_threshold_bin<SORT_THREADS, 64>(kept_hist, k, s_warp, &s_bin);
+    {
+        int4* hp = reinterpret_cast<int4*>(kept_hist) + t * 16;
+#pragma unroll
+        for (int q = 0; q < 16; q++) hp[q] = make_int4(0, 0, 0, 0);
+    }
+    // 2. gather the keys at or above that bin
+    if (t == 0) s_fill = 0;
+    __syncthreads();
+    // count first (cheap: the list is L2 resident) to choose shared memory or the global spill
+    int mine = 0;
+    for (int i = t; i < n; i += SORT_THREADS) mine += ((unsigned)(accepted[i] >> 48) >= thr) ? 1 : 0;
+    if (mine) atomicAdd(&s_fill, mine);
+    __syncthreads();
+    const int m = s_fill;
+    int P = 1;
+    while (P < m) P <<= 1;
+    unsigned long long* arr = (P <= SORT_SMEM_KEYS) ? s_keys : spill;
+    // the spill buffer holds next_pow2(cand_cap) keys (csrc/abi/capi.cu), so P always fits
+    __syncthreads();
+    if (t == 0) s_fill = 0;
+    __syncthreads();
+    for (int base = 0; base < n; base += SORT_THREADS) {
         const int i = base + t;
         unsigned long long key = 0ull;
         bool keep = false;
         if (i < n) {
-            key = keys[i];
-            keep = key >= kth;
+            key = accepted[i];
+            keep = (unsigned)(key >> 48) >= thr;
         }
-        const unsigned m = __ballot_sync(0xffffffffu, keep);
-        int b = 0;
-        if (m) {
-            const int leader = __ffs(m) - 1;
-            if (lane == leader) b = atomicAdd(&s_out, __popc(m));
+        const unsigned bal = __ballot_sync(0xffffffffu, keep);
+        if (bal) {
+            const int lane = t & 31, leader = __ffs(bal) - 1;
+            int b = 0;
+            if (lane == leader) b = atomicAdd(&s_fill, __popc(bal));
             b = __shfl_sync(0xffffffffu, b, leader);
-            if (keep) {
-                const int slot = b + __popc(m & ((1u << lane) - 1));
-                if (slot < out_cap) out[slot] = key;
-            }
+            if (keep) arr[b + __popc(bal & ((1u << lane) - 1))] = key;
         }
+    }
+    for (int i = m + t; i < P; i += SORT_THREADS) arr[i] = 0ull;   // zero keys sort last
+    __syncthreads();
+    // 3. sort descending on (value, address) and emit the first k as keypoints
+    bitonic_sort_desc(arr, P);
+    if (t == 0) *kps_count = k;
+    for (int i = t; i < k; i += SORT_THREADS) {
+        const int addr = (int)(arr[i] & 0xffffffffu);
+        const int y = addr / w;
+        kps[2 * i] = (float)(addr - y * w);
+        kps[2 * i + 1] = (float)y;
     }
 }
 
@@ -264,7 +337,7 @@ size_t select_cub_temp_bytes(int cap) {
 
 static void launch_greedy(const unsigned long long* list, const int* count, int cap, const float* eig, int eig_pitch,
                           uint8_t* state, int state_pitch, int w, int h, double min_distance,
-                          const SelectWorkspace& ws, int* round_counters, int enough_at, int sm_count,
+                          const SelectWorkspace& ws, int* kept_hist, int* round_counters, int enough_at, int sm_count,
                           cudaStream_t s) {
     int R = (int)ceil(min_distance) - 1;
     double md2 = min_distance * min_distance;
@@ -275,7 +348,8 @@ static void launch_greedy(const unsigned long long* list, const int* count, int 
     int nblocks = sm_count * blocks_per_sm;
     void* args[] = {(void*)&list, (void*)&count, (void*)&cap, (void*)&eig, (void*)&eig_pitch, (void*)&state,
                     (void*)&state_pitch, (void*)&w, (void*)&h, (void*)&R, (void*)&md2, (void*)&ws.accepted,
-                    (void*)&ws.accepted_count, (void*)&round_counters, (void*)&ws.remaining, (void*)&enough_at};
+                    (void*)&ws.accepted_count, (void*)&kept_hist, (void*)&round_counters, (void*)&ws.remaining,
+                    (void*)&enough_at};
     cudaLaunchCooperativeKernel((void*)greedy_suppress_kernel, dim3(nblocks), dim3(256), args, 0, s);
 }
 
@@ -283,41 +357,44 @@ void launch_select(const unsigned long long* cand, const int* cand_count, int ca
                    int eig_pitch, uint8_t* state, int state_pitch, int w, int h, double min_distance,
                    int max_corners, SelectWorkspace ws, float* kps_out, int kps_cap, int* kps_count, int sm_count,
                    cudaStream_t s) {
+    cudaFuncSetAttribute(select_sort_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)(SORT_SMEM_KEYS * sizeof(unsigned long long)));   // per device, cheap
     cudaMemsetAsync(ws.accepted_count, 0, sizeof(int), s);
-    const bool limited = max_corners > 0 && max_corners <= ws.topk_cap;
+    const bool limited = max_corners > 0;
+    int* kept_hist = limited ? ws.kept_hist : nullptr;
     // the unlimited path sorts the whole accepted[] buffer: unused slots must be zero (they sort last)
     if (!limited) cudaMemsetAsync(ws.accepted, 0, sizeof(unsigned long long) * (size_t)ws.cap, s);
     if (min_distance >= 1.0) {
         cudaMemsetAsync(ws.round_counters, 0, sizeof(int) * 2 * kMaxGreedyRounds, s);
         if (limited) {
             // pass 1: the strongest ~4*max_corners candidates
-            strong_threshold_kernel<<<1, 1024, 0, s>>>(ws.hist, 4 * max_corners, ws.sel);
-            compact_strong_kernel<<<sm_count, 256, 0, s>>>(cand, cand_count, cand_cap, ws.sel, ws.strong, ws.sel + 1);
+            cudaMemsetAsync(ws.sel, 0, sizeof(int) * 8, s);
+            compact_strong_kernel<<<sm_count * 4, 256, 0, s>>>(cand, cand_count, cand_cap, ws.hist, 4 * max_corners,
+                                                               ws.strong, ws.sel + 1);
             launch_greedy(ws.strong, ws.sel + 1, cand_cap, eig, eig_pitch, state, state_pitch, w, h, min_distance, ws,
-                          ws.round_counters, 0, sm_count, s);
+                          kept_hist, ws.round_counters, 0, sm_count, s);
             // pass 2 (no-op when pass 1 already kept max_corners corners): everything else
             launch_greedy(cand, cand_count, cand_cap, eig, eig_pitch, state, state_pitch, w, h, min_distance, ws,
-                          ws.round_counters + kMaxGreedyRounds, max_corners, sm_count, s);
+                          kept_hist, ws.round_counters + kMaxGreedyRounds, max_corners, sm_count, s);
         } else {
             launch_greedy(cand, cand_count, cand_cap, eig, eig_pitch, state, state_pitch, w, h, min_distance, ws,
-                          ws.round_counters, 0, sm_count, s);
+                          kept_hist, ws.round_counters, 0, sm_count, s);
         }
     } else {
         accept_all_kernel<<<sm_count * 2, 256, 0, s>>>(cand, cand_count, cand_cap, ws.accepted, ws.accepted_count,
-                                                       ws.remaining);
+                                                       kept_hist, ws.remaining);
     }
     // keys: [63:32] ordered value, [31:0] address (< w*h); zero keys sort last
-    size_t temp = ws.cub_temp_bytes;
-    const unsigned long long* sorted = ws.sorted;
     if (limited) {
-        topk_select_kernel<<<1, 1024, 0, s>>>(ws.accepted, ws.accepted_count, max_corners, ws.topk, max_corners);
-        cub::DeviceRadixSort::SortKeysDescending(ws.cub_temp, temp, ws.topk, ws.sorted, max_corners, 0, 64, s);
+        select_sort_emit_kernel<<<1, SORT_THREADS, SORT_SMEM_KEYS * sizeof(unsigned long long), s>>>(
+            ws.accepted, ws.accepted_count, ws.kept_hist, max_corners, ws.sorted, ws.sorted_cap, w, kps_out, kps_cap,
+            kps_count);
     } else {
+        size_t temp = ws.cub_temp_bytes;
         cub::DeviceRadixSort::SortKeysDescending(ws.cub_temp, temp, ws.accepted, ws.sorted, ws.cap, 0, 64, s);
+        keys_to_keypoints_kernel<<<(kps_cap + 255) / 256, 256, 0, s>>>(ws.sorted, ws.accepted_count, w, max_corners,
+                                                                       kps_out, kps_cap, kps_count);
     }
-    const int nthreads = max_corners > 0 ? (max_corners < kps_cap ? max_corners : kps_cap) : kps_cap;
-    keys_to_keypoints_kernel<<<(nthreads + 255) / 256, 256, 0, s>>>(sorted, ws.accepted_count, w, max_corners, kps_out,
-                                                                    kps_cap, kps_count);
 }
 
 }  // namespace pc
