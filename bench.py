@@ -178,6 +178,7 @@ def main():
     ap.add_argument("--cpu-baseline-frames", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-track", action="store_true", help="time detect+LK only (no per-frame PnP sweep)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -185,9 +186,12 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     w, h, max_corners, clip_frames = CONFIGS[args.config]
     fps = args.frames_per_step
-    metric = "frame-pairs/s (detect+LK) at %s" % {"4k": "4K", "1080p": "1080p", "720p": "720p"}[args.config]
+    track = not args.no_track
+    stages = "detect+LK+PnP" if track else "detect+LK"
+    metric = "frame-pairs/s (%s) at %s" % (stages, {"4k": "4K", "1080p": "1080p", "720p": "720p"}[args.config])
     config = {"workload": f"{args.config} synthetic clip, {max_corners} features/frame, detect+pyramid+LK "
-                          f"(+-1,2,4,8 neighbours), {fps} frames/step",
+                          f"(+-1,2,4,8 neighbours)" + (" + forward PnP sweep (ray cast + LM per frame)" if track else "")
+                          + f", {fps} frames/step",
               "width": w, "height": h, "max_corners": max_corners, "frames_per_step": fps,
               "parallelism": f"frames sharded x{world}" if world > 1 else "single GPU",
               "l2_policy": "inputs larger than L2 (each step streams fresh frames)"}
@@ -238,26 +242,89 @@ def main():
     gftt = capi.default_gftt(max_corners=max_corners)
     flow = capi.default_flow()
 
-    def run_steps(n_steps: int, start_frame_idx: int, mem_kind: int, base_ptr: int, ring: int, download: bool):
+    def image_of(idx: int, ring: int) -> int:
+        """Frame index -> resident image: a triangle wave over the ring, so consecutive frames are
+        always consecutive images of the camera path (no motion jump where the ring wraps)."""
+        if idx < ring:
+            return idx
+        period = 2 * (ring - 1)
+        m = idx % period
+        return m if m < ring else period - m
+
+    # ---- Track (tracker.cc:36-213): forward PnP sweep fed by the flows as they are produced ----
+    # A second context owns the mesh and the PnP scratch so that its (host-synchronous) calls run
+    # on their own stream next to the analyzer's queued kernels.
+    trk = None
+    if track:
+        trk = capi.Context(device=local_rank, max_width=64, max_height=64, max_features=1024)
+        verts, tris = synth.plane_mesh(w, h, scale)
+        trk.mesh_set(verts, tris)
+    bundle = capi.default_bundle()
+    model = np.eye(4, dtype=np.float32)
+
+    class Sweep:
+        """State of one forward sweep: keypoints / tracked cameras of the last 9 frames."""
+
+        def __init__(self, ring: int):
+            self.ring = ring
+            self.kps = {}
+            self.cams = {}
+            self.tracked = 0
+            self.matches = 0
+            self.max_t_err = 0.0
+
+        def truth(self, idx: int):
+            i = image_of(idx, self.ring)
+            return capi.camera_state(K, Rs[i], ts[i])
+
+        def consume(self, r, timed: bool):
+            """r: one analyze_pop result (views into pinned buffers, valid until the next pop)."""
+            f = r["frame_id"]
+            idx = f - (first - 8)
+            self.kps[f] = r["keypoints"].copy()
+            sources = []
+            for (a, b, rows, sidx, tgt, err) in r["pairs"]:
+                if b == f and a < f and rows and a in self.cams:
+                    sources.append((self.cams[a], self.kps[a], sidx, tgt))
+            if sources:
+                init = self.cams.get(f - 1) or self.truth(idx)
+                cam, st, inl, m = trk.track_frame(sources, model, init, bundle)
+                self.cams[f] = cam
+                if timed:
+                    self.tracked += 1
+                    self.matches += m
+                    i = image_of(idx, self.ring)
+                    self.max_t_err = max(self.max_t_err, float(np.abs(np.array(cam.t[:]) - ts[i]).max()))
+            else:
+                self.cams[f] = self.truth(idx)               # sweep start: known pose
+            for d in (self.kps, self.cams):
+                d.pop(f - 9, None)
+
+    def run_steps(n_steps: int, start_frame_idx: int, mem_kind: int, base_ptr: int, ring: int, download: bool,
+                  sweep=None, timed=False):
         """Pushes n_steps*fps frames (cycling over `ring` resident buffers) and pops results."""
         pairs = 0
         rows = 0
         idx = start_frame_idx
         for _ in range(n_steps * fps):
-            ctx.analyze_push(first - 8 + idx, base_ptr + (idx % ring) * frame_bytes, stride, mem_kind)
+            ctx.analyze_push(first - 8 + idx, base_ptr + image_of(idx, ring) * frame_bytes, stride, mem_kind)
             idx += 1
             if ctx.analyze_pending() >= 4:
                 r = ctx.analyze_pop(download=download, copy=False)
                 pairs += len(r["pairs"])
                 rows += sum(p[2] for p in r["pairs"])
+                if sweep is not None:
+                    sweep.consume(r, timed)
         return pairs, rows, idx
 
-    def drain(download: bool):
+    def drain(download: bool, sweep=None, timed=False):
         pairs = rows = 0
         while ctx.analyze_pending():
             r = ctx.analyze_pop(download=download, copy=False)
             pairs += len(r["pairs"])
             rows += sum(p[2] for p in r["pairs"])
+            if sweep is not None:
+                sweep.consume(r, timed)
         return pairs, rows
 
     def barrier():
@@ -267,27 +334,34 @@ def main():
         torch.cuda.synchronize()
 
     def timed_leg(mem_kind: int, base_ptr: int, ring: int, download: bool):
+        download = download or track                         # the tracker consumes host flow rows
+        sweep = Sweep(ring) if track else None
         ctx.analyze_begin(w, h, first - 8, 10 ** 6, gftt, flow)
         ctx.analyze_set_halo(8)
         idx = 0
         for _ in range(8):                                   # halo frames of the previous shard
-            ctx.analyze_push(first - 8 + idx, base_ptr + (idx % ring) * frame_bytes, stride, mem_kind)
+            ctx.analyze_push(first - 8 + idx, base_ptr + image_of(idx, ring) * frame_bytes, stride, mem_kind)
             idx += 1
             if ctx.analyze_pending() >= 4:
-                ctx.analyze_pop(download=False)
-        _, _, idx = run_steps(args.warmup, idx, mem_kind, base_ptr, ring, download)
-        drain(download)
+                r = ctx.analyze_pop(download=download, copy=False)
+                if sweep is not None:
+                    sweep.consume(r, False)
+        _, _, idx = run_steps(args.warmup, idx, mem_kind, base_ptr, ring, download, sweep)
+        drain(download, sweep)
         ctx.timing_read(reset=True)
         ctx.timing_enable(True)
-        launches0 = ctx.kernel_launches()
+        if trk:
+            trk.timing_read(reset=True)
+            trk.timing_enable(True)
+        launches0 = ctx.kernel_launches() + (trk.kernel_launches() if trk else 0)
         sampler = ClockSampler(local_rank)
         barrier()
         sampler.start()
         ctx.mark(0)
         t0 = time.perf_counter()
-        pairs, rows, idx = run_steps(args.steps, idx, mem_kind, base_ptr, ring, download)
-        p2, r2 = drain(download)
-        ctx.mark(1)
+        pairs, rows, idx = run_steps(args.steps, idx, mem_kind, base_ptr, ring, download, sweep, True)
+        p2, r2 = drain(download, sweep, True)                # the last track call is host-synchronous,
+        ctx.mark(1)                                          # so mark 1 is recorded after all the work
         ctx.synchronize()
         barrier()
         wall = time.perf_counter() - t0
@@ -295,10 +369,20 @@ def main():
         dev_ms = ctx.elapsed_ms(0, 1)
         times = ctx.timing_read(reset=True)
         ctx.timing_enable(False)
-        launches = ctx.kernel_launches() - launches0
+        if trk:
+            tt = trk.timing_read(reset=True)
+            trk.timing_enable(False)
+            for key, val in tt.items():
+                times[key] = times.get(key, 0) + val
+        launches = ctx.kernel_launches() + (trk.kernel_launches() if trk else 0) - launches0
         ctx.analyze_end()
-        return dict(pairs=pairs + p2, rows=rows + r2, dev_ms=dev_ms, wall_s=wall, clocks=clocks, times=times,
-                    launches=launches)
+        out = dict(pairs=pairs + p2, rows=rows + r2, dev_ms=dev_ms, wall_s=wall, clocks=clocks, times=times,
+                   launches=launches)
+        if sweep is not None:
+            out["track"] = {"frames_tracked": sweep.tracked,
+                            "matches_per_frame": sweep.matches / max(sweep.tracked, 1),
+                            "max_abs_translation_error": sweep.max_t_err}
+        return out
 
     # ---- value: inputs resident in HBM, results stay on device --------------------------
     res = timed_leg(capi.PC_MEM_DEVICE, dev_frames, n_frames, download=False)
@@ -306,7 +390,7 @@ def main():
     # ---- e2e: pinned host frames in, rows out -------------------------------------------
     e2e = None
     if not args.no_e2e:
-        ring = 24
+        ring = 32
         host_ptr = ctx.pinned_alloc(frame_bytes * ring)
         import ctypes
         for i in range(ring):                                # fill the pinned ring from the device clip
@@ -338,6 +422,8 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "u8/int32/f32", "data": "synthetic",
             "config": config, "clocks": res["clocks"], "gpu_launches": int(res["launches"]),
             "wall_s": res["wall_s"], "pairs": int(total_pairs)}
+    if "track" in res:
+        line["track"] = res["track"]
     if e2e is not None:
         e_s = reduce_max(e2e["dev_ms"]) * 1e-3
         e_pairs = reduce_sum(e2e["pairs"])
@@ -346,6 +432,8 @@ def main():
                        "h2d_bytes_per_step": int(frame_bytes * fps),
                        "d2h_bytes_per_step": int(rows_per_step * 16 + fps * max_corners * 8),
                        "wall_s": e2e["wall_s"], "clocks": e2e["clocks"]}
+        if "track" in e2e:
+            line["e2e"]["track"] = e2e["track"]
 
     # ---- roofline of the dominant kernel (rank 0's numbers) ------------------------------
     peak, peak_src = read_peak_hbm()
@@ -361,6 +449,10 @@ def main():
         "select": 4 * w * h + 8 * max_corners,
         "compact": 8 * max_corners * 13 + 8 * int(n_out) * 16,
     }
+    if "track" in res:                                    # 20 B per match, read once per pass
+        m_frame = res["track"]["matches_per_frame"]
+        per_launch["raycast"] = int(20 * m_frame)
+        per_launch["pnp"] = int(20 * m_frame)
     dom_ms, dom_n = fam[dominant]
     avg_ms = dom_ms / max(dom_n, 1)
     achieved = per_launch.get(dominant, 0) / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0
@@ -389,6 +481,8 @@ def main():
     if rank == 0:
         print(json.dumps(line))
     ctx.device_free(dev_frames)
+    if trk:
+        trk.close()
     ctx.close()
 
 

@@ -133,7 +133,7 @@ static int validate_gftt_opts(pc_ctx* c, const pc_gftt_opts* o) {
     PC_CHECK(c, o->block_size == 3 && o->gradient_size == 3, "only block_size 3 / gradient_size 3 are built");
     PC_CHECK(c, !o->use_harris, "use_harris is out of scope (never enabled by the addon)");
     const int gr = std::max(1, o->grid_rows), gc = std::max(1, o->grid_cols);
-    PC_CHECK(c, gr * gc <= c->cell_cap, "grid_rows*grid_cols too large");
+    PC_CHECK(c, gr * gc <= c->cell_cap, "grid_rows*grid_cols too large (limit 1024)");
     return PC_OK;
 }
 
@@ -354,7 +354,7 @@ int pc_create(const pc_limits* limits, pc_ctx** out) {
     PC_CUDA(nullptr, cudaMalloc(&cp->eig, sizeof(float) * (size_t)cp->eig_pitch * H));
     cp->state_pitch = (W + 127) / 128 * 128;
     PC_CUDA(nullptr, cudaMalloc(&cp->state, (size_t)cp->state_pitch * H));
-    cp->cell_cap = 4096;
+    cp->cell_cap = 1024;      // = NMS_MAX_CELLS (mineig.cu)
     PC_CUDA(nullptr, cudaMalloc(&cp->cell_max, sizeof(int) * cp->cell_cap));
     // 3x3 NMS leaves at most one candidate per 2x2 block except on plateaus; w*h/4 is ample
     cp->cand_cap = std::max(1024, (int)(((size_t)W * H) / 4));

@@ -42,7 +42,7 @@ void launch_nms_candidates(const float* eig, int eig_pitch, int w, int h, Detect
 // ---- K6/K7: greedy min-distance suppression + ordering (select.cu) --------------------
 struct SelectWorkspace {
     unsigned long long* accepted;      // cap entries
-    unsigned long long* sorted;        // sorted_cap = next_pow2(cap) entries (sort output / bitonic spill)
+    unsigned long long* sorted;        // sorted_cap >= cap entries (CUB sort output, unlimited path)
     unsigned long long* strong;        // cap entries: the strongest candidates (max_corners > 0 path)
     int* accepted_count;               // device int
     int* round_counters;               // 2 * kMaxGreedyRounds ints

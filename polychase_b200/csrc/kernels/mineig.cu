@@ -18,11 +18,12 @@
 // changes ~2 pixels per million by a few ulp.  This kernel forms each 3x3 sum
 // independently (the correctly rounded value).
 //
-// Layout (HBM-streaming, no shared memory): one warp owns a 120-column x 32-row output tile and
-// marches down it.  Each lane holds 4 adjacent columns (one aligned 32-bit gray load per row,
-// one aligned 16-byte eig store per row); the +-1 column neighbours come from the adjacent
-// lanes by shuffle, the +-1 row neighbours are rolling registers.  Lanes 0 and 31 only feed
-// their neighbours (the 4+4 halo columns of the tile).
+// Layout (HBM-streaming, no shared memory): one warp owns a (30*NC)-column x 32-row output tile
+// and marches down it.  Each lane holds NC adjacent columns (one aligned gray load per row, one
+// aligned eig vector store per row); the +-1 column neighbours come from the adjacent lanes by
+// shuffle, the +-1 row neighbours are rolling registers.  Lanes 0 and 31 only feed their
+// neighbours (the halo columns of the tile).  NC = 2 keeps the rolling state (24 floats + 12
+// doubles per lane) small enough for 24 resident warps per SM.
 //
 // Rows outside the image: the march simply continues over the REFLECT_101 row indices.  For
 // the one row each side that the box filter needs (cov row -1 := cov row 1, cov row h := cov
@@ -34,84 +35,100 @@
 
 namespace pc {
 
-constexpr int ME_COLS = 120;     // output columns per warp tile
-constexpr int ME_ROWS = 32;      // output rows per warp tile
+constexpr int ME_NC = 2;                       // columns per lane
+constexpr int ME_COLS = 30 * ME_NC;            // output columns per warp tile (lanes 1..30)
+constexpr int ME_ROWS = 32;                    // output rows per warp tile
 constexpr int ME_WARPS = 4;
 
 __device__ __forceinline__ int cell_of(int x, int y, const DetectGrid& g) {
     return (y / g.block_h) * g.grid_cols + (x / g.block_w);
 }
 
-__device__ __forceinline__ uint32_t load_gray4(const uint8_t* __restrict__ gray, int w, int h, int pitch, int x,
-                                               int gy_logical, bool fast) {
+// ME_NC gray bytes of this lane's columns (packed little-endian), REFLECT_101 in both directions
+__device__ __forceinline__ uint32_t load_gray(const uint8_t* __restrict__ gray, int w, int h, int pitch, int x,
+                                              int gy_logical, bool fast) {
     const uint8_t* row = gray + (size_t)reflect101(gy_logical, h) * pitch;
-    if (fast) return __ldg(reinterpret_cast<const uint32_t*>(row + x));
-    return (uint32_t)row[reflect101(x, w)] | ((uint32_t)row[reflect101(x + 1, w)] << 8) |
-           ((uint32_t)row[reflect101(x + 2, w)] << 16) | ((uint32_t)row[reflect101(x + 3, w)] << 24);
+    if (fast) {
+        if (ME_NC == 4) return __ldg(reinterpret_cast<const uint32_t*>(row + x));
+        return __ldg(reinterpret_cast<const uint16_t*>(row + x));
+    }
+    uint32_t v = 0;
+#pragma unroll
+    for (int j = 0; j < ME_NC; j++) v |= (uint32_t)row[reflect101(x + j, w)] << (8 * j);
+    return v;
 }
 
-__global__ void __launch_bounds__(ME_WARPS * 32) min_eig_kernel(const uint8_t* __restrict__ gray, int w, int h,
-                                                                int pitch, float* __restrict__ eig, int eig_pitch,
-                                                                DetectGrid grid, int* __restrict__ cell_max,
-                                                                int tiles_x, int tiles_y) {
+__global__ void __launch_bounds__(ME_WARPS * 32, ME_NC == 2 ? 6 : 4)
+min_eig_kernel(const uint8_t* __restrict__ gray, int w, int h, int pitch, float* __restrict__ eig, int eig_pitch,
+               DetectGrid grid, int* __restrict__ cell_max, int tiles_x, int tiles_y) {
+    constexpr int NC = ME_NC;
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const int tile = blockIdx.x * ME_WARPS + (threadIdx.x >> 5);
     if (tile >= tiles_x * tiles_y) return;
     const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
-    const int xb = tx * ME_COLS - 4 + 4 * lane;          // this lane's columns xb .. xb+3 (xb % 4 == 0)
+    const int xb = tx * ME_COLS - NC + NC * lane;          // this lane's columns xb .. xb+NC-1 (xb % NC == 0)
     const int y0 = ty * ME_ROWS;
     const int y_end = min(y0 + ME_ROWS, h);
     const float s = (float)(1.0 / (4.0 * 3.0 * 255.0));
     const float s2 = 2.0f * s;
     const int wvec = (w / 32) * 32;
-    const bool fast = xb >= 0 && xb + 3 < w;
-    const bool live = xb + 3 >= -1 && xb <= w;             // lanes whose columns can matter at all
+    const bool fast = xb >= 0 && xb + NC - 1 < w;
+    const bool live = xb + NC >= 0 && xb <= w;             // lanes whose columns can matter at all
     const bool out_lane = lane >= 1 && lane <= 30 && xb < w;
     const int jr = (w - 1) - xb;                            // position of the last image column in this lane
+    // warp-uniform special cases (tile_x0 .. tile_x0 + 32*NC - 1 are the columns the warp touches)
+    const int tile_x0 = tx * ME_COLS - NC;
+    const bool tail_tile = tile_x0 + 32 * NC > wvec;        // some column uses the non-FMA row filter
+    const bool left_tile = tile_x0 < 0, right_tile = tile_x0 + 32 * NC >= w;
 
     // grid cell bookkeeping: the common case is one cell column per warp tile
-    int cx[4];
+    int cx[NC];
 #pragma unroll
-    for (int j = 0; j < 4; j++) cx[j] = min(max(xb + j, 0), w - 1) / grid.block_w;
+    for (int j = 0; j < NC; j++) cx[j] = min(max(xb + j, 0), w - 1) / grid.block_w;
     const int cx_ref = __shfl_sync(FULL, cx[0], 1);
-    const bool my_uniform = !out_lane || (cx[0] == cx_ref && cx[3] == cx_ref);
+    const bool my_uniform = !out_lane || (cx[0] == cx_ref && cx[NC - 1] == cx_ref);
     const bool uniform_x = __all_sync(FULL, my_uniform);
-    int run_max = (int)0x80000000, run_cy = y0 / grid.block_h;
+    // eig >= -tiny and never NaN, so a float max is enough for the running cell maximum
+    float run_max = -INFINITY;
+    int run_cy = y0 / grid.block_h;
+    int next_cy_y = (run_cy + 1) * grid.block_h;            // first row of the next cell row
 
-    float rx[3][4], rsm[3][4];                 // rolling horizontal passes (rows k-2, k-1, k)
-    double Rp[3][4], T[3][4];                  // rowsum of the previous cov row, and prev-prev + prev
+    float rx[3][NC], rsm[3][NC];               // rolling horizontal passes (rows k-2, k-1, k)
+    double Rp[3][NC], T[3][NC];                // rowsum of the previous cov row, and prev-prev + prev
 #pragma unroll
     for (int c = 0; c < 3; c++)
 #pragma unroll
-        for (int j = 0; j < 4; j++) { Rp[c][j] = 0.0; T[c][j] = 0.0; }
+        for (int j = 0; j < NC; j++) { Rp[c][j] = 0.0; T[c][j] = 0.0; }
 #pragma unroll
     for (int r = 0; r < 3; r++)
 #pragma unroll
-        for (int j = 0; j < 4; j++) { rx[r][j] = 0.f; rsm[r][j] = 0.f; }
+        for (int j = 0; j < NC; j++) { rx[r][j] = 0.f; rsm[r][j] = 0.f; }
 
-    uint32_t word = live ? load_gray4(gray, w, h, pitch, xb, y0 - 2, fast) : 0u;
+    uint32_t word = live ? load_gray(gray, w, h, pitch, xb, y0 - 2, fast) : 0u;
     const int steps = (y_end - y0) + 4;
+#pragma unroll 1
     for (int k = 0; k < steps; k++) {
         // prefetch the next gray row while this one is processed
         uint32_t next_word = 0u;
-        if (live && k + 1 < steps) next_word = load_gray4(gray, w, h, pitch, xb, y0 - 1 + k, fast);
+        if (live && k + 1 < steps) next_word = load_gray(gray, w, h, pitch, xb, y0 - 1 + k, fast);
 
         // ---- horizontal pass on gray row (logical) y0 - 2 + k ---------------------------------
         const uint32_t wl = __shfl_up_sync(FULL, word, 1), wr = __shfl_down_sync(FULL, word, 1);
-        float p[6];
-        p[0] = (float)(wl >> 24);
-        p[1] = (float)(word & 255u); p[2] = (float)((word >> 8) & 255u);
-        p[3] = (float)((word >> 16) & 255u); p[4] = (float)(word >> 24);
-        p[5] = (float)(wr & 255u);
+        float p[NC + 2];
+        p[0] = (float)((wl >> (8 * (NC - 1))) & 255u);
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
+        for (int j = 0; j < NC; j++) p[j + 1] = (float)((word >> (8 * j)) & 255u);
+        p[NC + 1] = (float)(wr & 255u);
+#pragma unroll
+        for (int j = 0; j < NC; j++) {
             rx[0][j] = rx[1][j]; rx[1][j] = rx[2][j];
             rsm[0][j] = rsm[1][j]; rsm[1][j] = rsm[2][j];
             const float pm = p[j], pc_ = p[j + 1], pp = p[j + 2];
             rx[2][j] = __fsub_rn(pp, pm);
-            rsm[2][j] = (xb + j < wvec) ? __fmaf_rn(pp, s, __fmaf_rn(pc_, s2, __fmul_rn(pm, s)))
-                                        : __fadd_rn(__fadd_rn(__fmul_rn(pm, s), __fmul_rn(pc_, s2)), __fmul_rn(pp, s));
+            rsm[2][j] = __fmaf_rn(pp, s, __fmaf_rn(pc_, s2, __fmul_rn(pm, s)));
+            if (tail_tile && xb + j >= wvec)
+                rsm[2][j] = __fadd_rn(__fadd_rn(__fmul_rn(pm, s), __fmul_rn(pc_, s2)), __fmul_rn(pp, s));
         }
         word = next_word;
         if (k < 2) continue;
@@ -119,9 +136,9 @@ __global__ void __launch_bounds__(ME_WARPS * 32) min_eig_kernel(const uint8_t* _
         // ---- cov row (logical) cy = y0 - 3 + k ------------------------------------------------
         const int cy = y0 - 3 + k;
         const bool flip = cy < 0 || cy >= h;                // mirrored window: dy came out negated
-        float c[3][4];
+        float c[3][NC];
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
+        for (int j = 0; j < NC; j++) {
             const float dx = __fmaf_rn(__fadd_rn(rx[0][j], rx[2][j]), s, __fmul_rn(rx[1][j], s2));
             const float dy = __fsub_rn(rsm[2][j], rsm[0][j]);
             c[0][j] = __fmul_rn(dx, dx);
@@ -130,29 +147,29 @@ __global__ void __launch_bounds__(ME_WARPS * 32) min_eig_kernel(const uint8_t* _
             c[2][j] = __fmul_rn(dy, dy);
         }
         // ---- 3-tap horizontal sums in double, REFLECT_101 of cov at the image's side borders --
-        double R[3][4];
+        double R[3][NC];
 #pragma unroll
         for (int ch = 0; ch < 3; ch++) {
-            double d[6];
-            d[0] = (double)__shfl_up_sync(FULL, c[ch][3], 1);
-            d[5] = (double)__shfl_down_sync(FULL, c[ch][0], 1);
+            double d[NC + 2];
+            d[0] = (double)__shfl_up_sync(FULL, c[ch][NC - 1], 1);
+            d[NC + 1] = (double)__shfl_down_sync(FULL, c[ch][0], 1);
 #pragma unroll
-            for (int j = 0; j < 4; j++) d[j + 1] = (double)c[ch][j];
-            if (xb == 0) d[0] = d[2];                       // cov[-1] := cov[1]
-            if ((unsigned)jr < 4u) {                        // cov[w] := cov[w-2]
+            for (int j = 0; j < NC; j++) d[j + 1] = (double)c[ch][j];
+            if (left_tile && xb == 0) d[0] = d[2];          // cov[-1] := cov[1]
+            if (right_tile && (unsigned)jr < (unsigned)NC) {   // cov[w] := cov[w-2]
 #pragma unroll
-                for (int j = 0; j < 4; j++)
+                for (int j = 0; j < NC; j++)
                     if (j == jr) d[j + 2] = d[j];
             }
 #pragma unroll
-            for (int j = 0; j < 4; j++) R[ch][j] = __dadd_rn(__dadd_rn(d[j], d[j + 1]), d[j + 2]);
+            for (int j = 0; j < NC; j++) R[ch][j] = __dadd_rn(__dadd_rn(d[j], d[j + 1]), d[j + 2]);
         }
         // ---- 3-tap vertical sums, eigenvalue, store (output row y = cy - 1) --------------------
         const int y = cy - 1;
-        if (k >= 4 && y < h) {
-            float v[4];
+        if (k >= 4) {
+            float v[NC];
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
+            for (int j = 0; j < NC; j++) {
                 const float sxx = (float)__dadd_rn(T[0][j], R[0][j]);
                 const float sxy = (float)__dadd_rn(T[1][j], R[1][j]);
                 const float syy = (float)__dadd_rn(T[2][j], R[2][j]);
@@ -160,45 +177,48 @@ __global__ void __launch_bounds__(ME_WARPS * 32) min_eig_kernel(const uint8_t* _
                 const float t = __fsub_rn(a, cc);
                 v[j] = __fsub_rn(__fadd_rn(a, cc), __fsqrt_rn(__fadd_rn(__fmul_rn(t, t), __fmul_rn(b, b))));
             }
-            const int cyc = y / grid.block_h;
-            if (cyc != run_cy) {                            // warp-uniform: the tile crossed a cell row
+            if (y >= next_cy_y) {                           // warp-uniform: the tile crossed a cell row
                 if (uniform_x) {
-                    const int m = __reduce_max_sync(FULL, run_max);
-                    if (lane == 0 && m != (int)0x80000000) atomicMax(&cell_max[run_cy * grid.grid_cols + cx_ref], m);
+                    const int m = __reduce_max_sync(FULL, float_to_ordered_int(run_max));
+                    if (lane == 0 && m != float_to_ordered_int(-INFINITY))
+                        atomicMax(&cell_max[run_cy * grid.grid_cols + cx_ref], m);
                 }
-                run_max = (int)0x80000000;
-                run_cy = cyc;
+                run_max = -INFINITY;
+                run_cy = y / grid.block_h;
+                next_cy_y = (run_cy + 1) * grid.block_h;
             }
             if (out_lane) {
                 float* dst = eig + (size_t)y * eig_pitch + xb;
-                if (xb + 3 < w) {
-                    *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+                if (xb + NC - 1 < w) {
+                    if (NC == 4) *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[NC - 2], v[NC - 1]);
+                    else *reinterpret_cast<float2*>(dst) = make_float2(v[0], v[1]);
                 } else {
 #pragma unroll
-                    for (int j = 0; j < 4; j++)
+                    for (int j = 0; j < NC; j++)
                         if (xb + j < w) dst[j] = v[j];
                 }
+                if (uniform_x) {
 #pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    if (xb + j < w) {
-                        const int ov = float_to_ordered_int(v[j]);
-                        if (uniform_x) run_max = max(run_max, ov);
-                        else atomicMax(&cell_max[cyc * grid.grid_cols + cx[j]], ov);
-                    }
+                    for (int j = 0; j < NC; j++)
+                        if (!right_tile || xb + j < w) run_max = fmaxf(run_max, v[j]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < NC; j++)
+                        if (xb + j < w) atomicMax(&cell_max[run_cy * grid.grid_cols + cx[j]], float_to_ordered_int(v[j]));
                 }
             }
         }
 #pragma unroll
         for (int ch = 0; ch < 3; ch++)
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
+            for (int j = 0; j < NC; j++) {
                 T[ch][j] = __dadd_rn(Rp[ch][j], R[ch][j]);
                 Rp[ch][j] = R[ch][j];
             }
     }
     if (uniform_x) {
-        const int m = __reduce_max_sync(FULL, run_max);
-        if (lane == 0 && m != (int)0x80000000) atomicMax(&cell_max[run_cy * grid.grid_cols + cx_ref], m);
+        const int m = __reduce_max_sync(FULL, float_to_ordered_int(run_max));
+        if (lane == 0 && m != float_to_ordered_int(-INFINITY)) atomicMax(&cell_max[run_cy * grid.grid_cols + cx_ref], m);
     }
 }
 
@@ -230,7 +250,8 @@ void launch_min_eig(Image8 gray, float* eig, int eig_pitch, DetectGrid g, int* c
 // per row) and appends candidates (warp-aggregated).
 constexpr int NMS_ROWS = 16;
 constexpr int NMS_WARPS = 4;
-constexpr int NMS_MAX_CELLS = 4096;    // = pc_ctx::cell_cap
+constexpr int NMS_MAX_CELLS = 1024;    // grid_rows * grid_cols limit (validated in csrc/abi/capi.cu)
+constexpr int NMS_STAGE = 512;         // candidate keys staged per warp before one global append
 
 __global__ void __launch_bounds__(NMS_WARPS * 32) nms_candidates_kernel(
     const float* __restrict__ eig, int eig_pitch, int w, int h, DetectGrid grid, const int* __restrict__ cell_max,
@@ -238,17 +259,30 @@ __global__ void __launch_bounds__(NMS_WARPS * 32) nms_candidates_kernel(
     int* __restrict__ cand_count, int* __restrict__ value_hist, int tiles_x, int tiles_y) {
     const unsigned FULL = 0xffffffffu;
     __shared__ float thr_tab[NMS_MAX_CELLS];
+    __shared__ int s_hist[4096];                              // block-private copy of value_hist
+    __shared__ unsigned long long s_stage[NMS_WARPS][NMS_STAGE];
     const int ncell = grid.grid_rows * grid.grid_cols;
     for (int i = threadIdx.x; i < ncell; i += blockDim.x)
         thr_tab[i] = (float)((double)ordered_int_to_float(__ldg(&cell_max[i])) * quality);
+    for (int i = threadIdx.x; i < 4096; i += blockDim.x) s_hist[i] = 0;
     __syncthreads();
-    const int lane = threadIdx.x & 31;
-    const int tile = blockIdx.x * NMS_WARPS + (threadIdx.x >> 5);
-    if (tile >= tiles_x * tiles_y) return;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int tile = blockIdx.x * NMS_WARPS + wib;
+    const bool tile_ok = tile < tiles_x * tiles_y;            // warp-uniform
     const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
     const int xb = tx * 128 + 4 * lane;
-    const int y0 = ty * NMS_ROWS, y_end = min(y0 + NMS_ROWS, h);
-    const bool live = xb < w;
+    const int y0 = ty * NMS_ROWS, y_end = tile_ok ? min(y0 + NMS_ROWS, h) : y0;
+    const bool live = tile_ok && xb < w;
+    int fill = 0;                                             // staged keys of this warp (warp-uniform)
+    auto flush = [&]() {
+        int base = 0;
+        if (lane == 0 && fill) base = atomicAdd(cand_count, fill);
+        base = __shfl_sync(FULL, base, 0);
+        for (int i = lane; i < fill; i += 32)
+            if (base + i < cand_cap) cand[base + i] = s_stage[wib][i];
+        __syncwarp();
+        fill = 0;
+    };
     int cxj[6];                                   // cell column of x = xb-1 .. xb+4
 #pragma unroll
     for (int j = 0; j < 6; j++) cxj[j] = min(max(xb - 1 + j, 0), w - 1) / grid.block_w;
@@ -317,7 +351,8 @@ __global__ void __launch_bounds__(NMS_WARPS * 32) nms_candidates_kernel(
             else
                 for (int j = 0; j < 4 && xb + j < w; j++) sp[j] = (bits >> (8 * j)) & 1u;
         }
-        // warp-aggregated append (order inside the list is irrelevant: keys are sorted later)
+        // stage the row's candidates in shared memory (order inside the list is irrelevant: keys are
+        // sorted later); one global append per warp tile
         const int mine = (int)is_c[0] + (int)is_c[1] + (int)is_c[2] + (int)is_c[3];
         if (__any_sync(FULL, mine > 0)) {
             int incl = mine;
@@ -327,22 +362,27 @@ __global__ void __launch_bounds__(NMS_WARPS * 32) nms_candidates_kernel(
                 if (lane >= o) incl += n;
             }
             const int total = __shfl_sync(FULL, incl, 31);
-            int base = 0;
-            if (lane == 31) base = atomicAdd(cand_count, total);
-            base = __shfl_sync(FULL, base, 31);
-            int slot = base + incl - mine;
+            if (fill + total > NMS_STAGE) flush();
+            int slot = fill + incl - mine;
 #pragma unroll
             for (int j = 0; j < 4; j++) {
                 if (is_c[j]) {
                     const uint32_t ov = float_to_ordered_uint(b[j + 1]);
-                    if (slot < cand_cap) cand[slot] = ((unsigned long long)ov << 32) | (unsigned)(y * w + xb + j);
-                    slot++;
-                    atomicAdd(&value_hist[ov >> 20], 1);
+                    s_stage[wib][slot++] = ((unsigned long long)ov << 32) | (unsigned)(y * w + xb + j);
+                    atomicAdd(&s_hist[ov >> 20], 1);
                 }
             }
+            fill += total;
+            __syncwarp();
         }
 #pragma unroll
         for (int j = 0; j < 6; j++) { a[j] = b[j]; b[j] = c[j]; }
+    }
+    flush();
+    __syncthreads();
+    for (int i = threadIdx.x; i < 4096; i += blockDim.x) {
+        const int v = s_hist[i];
+        if (v) atomicAdd(&value_hist[i], v);
     }
 }
 

@@ -18,9 +18,9 @@
 // candidates, the fixed point is first run on the strongest ~4*max_corners candidates (a value
 // threshold from a 12-bit histogram); only if that yields fewer than max_corners kept corners
 // does a second pass process everything.  Kept keys are counted into a 16-bit-bin histogram
-// of their value as they are accepted; one CTA then finds the bin that holds the
-// max_corners-th strongest key, gathers the keys at or above it into shared memory, sorts them
-// (bitonic, (value, address) descending) and writes the first max_corners as keypoints.
+// of their value as they are accepted; the final kernel finds the bin that holds the
+// max_corners-th strongest key, gathers the keys at or above it into shared memory and ranks
+// them by counting ((value, address) descending): rank r < max_corners is keypoint r.
 // With max_corners == 0 every kept key is sorted (CUB radix sort).
 #include <cooperative_groups.h>
 #include <cub/device/device_radix_sort.cuh>
@@ -33,6 +33,7 @@ namespace cg = cooperative_groups;
 namespace pc {
 
 enum : uint8_t { ST_NONE = 0, ST_UNDECIDED = 1, ST_KEPT = 2, ST_REJECTED = 3 };
+constexpr int kGreedySpins = 48;
 
 __device__ __forceinline__ unsigned long long key_at(const float* __restrict__ eig, int eig_pitch, int w, int x,
                                                      int y) {
@@ -43,10 +44,12 @@ __device__ __forceinline__ unsigned long long key_at(const float* __restrict__ e
 // undecided stronger neighbour, ST_KEPT or ST_REJECTED.  R <= 4 takes the word-wide path: the
 // 9 rows x 3 aligned words that cover the disc's bounding box are loaded up front
 // (independent L2 loads), then only the non-zero state bytes are looked at.
+constexpr int kMaxBlockers = 4;
 __device__ __forceinline__ int decide(unsigned long long key, int x, int y, const float* __restrict__ eig,
                                       int eig_pitch, const uint8_t* state, int state_pitch, int w, int h, int R,
-                                      double md2) {
+                                      double md2, int (&blockers)[kMaxBlockers], int& num_blockers) {
     bool blocked = false;
+    num_blockers = 0;
     if (R <= 4) {
         const int xl = x - 4, wx0 = xl & ~3;                 // may be negative: masked below
         uint32_t wd[9][3];
@@ -81,6 +84,8 @@ __device__ __forceinline__ int decide(unsigned long long key, int x, int y, cons
                     if (key_at(eig, eig_pitch, w, nx, y + dy) > key) {
                         if (ns == ST_KEPT) return ST_REJECTED;
                         blocked = true;
+                        if (num_blockers < kMaxBlockers) blockers[num_blockers] = (y + dy) * state_pitch + nx;
+                        num_blockers++;
                     }
                 }
             }
@@ -98,6 +103,7 @@ __device__ __forceinline__ int decide(unsigned long long key, int x, int y, cons
                 if (key_at(eig, eig_pitch, w, nx, ny) > key) {
                     if (ns == ST_KEPT) return ST_REJECTED;
                     blocked = true;
+                    num_blockers = kMaxBlockers + 1;         // generic path: no blocker list
                 }
             }
         }
@@ -133,11 +139,28 @@ __global__ void __launch_bounds__(256) greedy_suppress_kernel(
             const int y = addr / w, x = addr - y * w;
             uint8_t* sp = state + (size_t)y * state_pitch + x;
             if (__ldcg(sp) != ST_UNDECIDED) continue;
-            const int d = decide(key, x, y, eig, eig_pitch, state, state_pitch, w, h, R, md2);
+            int blockers[kMaxBlockers], nb;
+            int d = decide(key, x, y, eig, eig_pitch, state, state_pitch, w, h, R, md2, blockers, nb);
+            if (d == 0 && nb <= kMaxBlockers) {
+                // The blockers are stronger candidates that other (co-resident) threads are deciding
+                // right now: watch just those few state bytes for a bounded time instead of paying
+                // a grid barrier + rescan per dependency level.  States only move UNDECIDED -> final,
+                // so "a blocker got KEPT" / "all blockers got REJECTED" are final answers too.
+                for (int spin = 0; spin < kGreedySpins && d == 0; spin++) {
+                    __nanosleep(200);
+                    bool pending = false;
+                    for (int k = 0; k < nb; k++) {
+                        const uint8_t ns = __ldcg(state + blockers[k]);
+                        if (ns == ST_KEPT) d = ST_REJECTED;
+                        else if (ns == ST_UNDECIDED) pending = true;
+                    }
+                    if (d == 0 && !pending) d = ST_KEPT;
+                }
+            }
             if (d == ST_REJECTED) {
-                *sp = ST_REJECTED;
+                *(volatile uint8_t*)sp = ST_REJECTED;
             } else if (d == ST_KEPT) {
-                *sp = ST_KEPT;
+                *(volatile uint8_t*)sp = ST_KEPT;
                 accepted[atomicAdd(accepted_count, 1)] = key;
                 if (kept_hist) atomicAdd(&kept_hist[(unsigned)(key >> 48)], 1);
             } else {
@@ -167,10 +190,11 @@ __global__ void accept_all_kernel(const unsigned long long* __restrict__ cand, c
 }
 
 // Block-wide "largest bin b whose suffix count reaches `want`" over a histogram in global memory,
-// PER_THREAD consecutive bins per thread (descending search).  Returns the bin, or 0 if the whole
-// histogram holds fewer than `want`.
+// PER_THREAD consecutive bins per thread (descending search; PER_THREAD <= 64).  Returns the bin
+// (0 if the whole histogram holds fewer than `want`) and, through *count_out, the number of
+// entries in bins >= that bin.
 template <int THREADS, int PER_THREAD>
-__device__ __forceinline__ int suffix_threshold_bin(const int* hist, int want, int* s_warp, int* s_bin) {
+__device__ __forceinline__ int suffix_threshold_bin(const int* hist, int want, int* s_warp, int* s_res, int* count_out) {
     const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
     const int4* hp = reinterpret_cast<const int4*>(hist) + t * (PER_THREAD / 4);
     int s = 0;
@@ -186,20 +210,39 @@ __device__ __forceinline__ int suffix_threshold_bin(const int* hist, int want, i
         if (lane + o < 32) v += nb;
     }
     if (lane == 0) s_warp[wid] = v;
-    if (t == 0) *s_bin = 0;
+    if (t == 0) { s_res[0] = -1; s_res[1] = 0; }
     __syncthreads();
     int above = 0;
     for (int q = wid + 1; q < THREADS / 32; q++) above += s_warp[q];
     const int suf_incl = v + above, suf_excl = suf_incl - s;
-    if (suf_excl < want && want <= suf_incl) {              // the boundary bin is in this thread's range
-        int acc = suf_excl;
-        for (int k = PER_THREAD - 1; k >= 0; k--) {
-            acc += __ldcg(hist + t * PER_THREAD + k);
-            if (acc >= want) { *s_bin = t * PER_THREAD + k; break; }
+    if (suf_excl < want && want <= suf_incl) { s_res[0] = t; s_res[1] = suf_excl; }   // boundary thread
+    if (t == 0) s_res[2] = suf_incl;                        // whole histogram
+    __syncthreads();
+    const int tb = s_res[0];
+    if (tb < 0) {                                           // fewer than `want` entries: take everything
+        *count_out = s_res[2];
+        return 0;
+    }
+    // the first warp resolves the boundary thread's bins: 2 per lane, suffix scan
+    if (wid == 0) {
+        const int excl = s_res[1];
+        const int b0 = 2 * lane < PER_THREAD ? __ldcg(hist + tb * PER_THREAD + 2 * lane) : 0;
+        const int b1 = 2 * lane + 1 < PER_THREAD ? __ldcg(hist + tb * PER_THREAD + 2 * lane + 1) : 0;
+        int sv = b0 + b1;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int nb = __shfl_down_sync(0xffffffffu, sv, o);
+            if (lane + o < 32) sv += nb;
         }
+        const int incl1 = excl + sv - b0;                   // entries in bins >= 2*lane+1 of thread tb
+        const int incl0 = excl + sv;                        // entries in bins >= 2*lane
+        const int excl1 = incl0 - b0 - b1;                  // entries in bins > 2*lane+1
+        if (excl1 < want && want <= incl1) { s_res[3] = tb * PER_THREAD + 2 * lane + 1; s_res[4] = incl1; }
+        else if (incl1 < want && want <= incl0) { s_res[3] = tb * PER_THREAD + 2 * lane; s_res[4] = incl0; }
     }
     __syncthreads();
-    return *s_bin;
+    *count_out = s_res[4];
+    return s_res[3];
 }
 
 // Strong candidates: those whose 12-bit value bin is at or above the bin at which the suffix
@@ -209,8 +252,9 @@ __global__ void __launch_bounds__(256) compact_strong_kernel(const unsigned long
                                                              const int* hist, int want,
                                                              unsigned long long* __restrict__ strong,
                                                              int* __restrict__ strong_count) {
-    __shared__ int s_warp[8], s_bin;
-    const unsigned thr = (unsigned)suffix_threshold_bin<256, 16>(hist, want, s_warp, &s_bin);
+    __shared__ int s_warp[8], s_res[8];
+    int strong_total;
+    const unsigned thr = (unsigned)suffix_threshold_bin<256, 16>(hist, want, s_warp, s_res, &strong_total);
     const int n = min(*cand_count, cand_cap);
     for (int base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
         const int i = base + threadIdx.x;
@@ -231,84 +275,71 @@ __global__ void __launch_bounds__(256) compact_strong_kernel(const unsigned long
     }
 }
 
-// ---- final selection: top max_corners kept keys, sorted, as keypoints (one CTA) --------------
-constexpr int SORT_THREADS = 1024;
-constexpr int SORT_SMEM_KEYS = 16384;                       // 128 KB of dynamic shared memory
+// ---- final selection: the max_corners strongest kept keys, in order, as keypoints -------------
+// Every CTA finds the 16-bit value bin that holds the k-th strongest kept key (k = min(max_corners,
+// kept)), gathers the m >= k keys at or above it into shared memory, and ranks its own share of
+// them by counting (rank = number of gathered keys that are larger; keys are unique), one warp per
+// key.  rank < k -> keypoint slot `rank`.  m is k plus the population of one fine bin, so the m^2
+// comparisons spread over the grid are a few microseconds, where a single-CTA sort was ~130 us.
+constexpr int RANK_THREADS = 1024;
+constexpr int RANK_SMEM_KEYS = 16384;                       // 128 KB of dynamic shared memory
 
-__device__ __forceinline__ void bitonic_sort_desc(unsigned long long* a, int P) {
-    for (int size = 2; size <= P; size <<= 1) {
-        for (int stride = size >> 1; stride > 0; stride >>= 1) {
-            for (int i = threadIdx.x; i < (P >> 1); i += SORT_THREADS) {
-                const int pos = 2 * i - (i & (stride - 1));
-                const unsigned long long u = a[pos], v = a[pos + stride];
-                const bool desc = (pos & size) == 0;
-                if (desc ? (u < v) : (u > v)) { a[pos] = v; a[pos + stride] = u; }
-            }
-            __syncthreads();
-        }
-    }
-}
-
-__global__ void __launch_bounds__(SORT_THREADS) select_sort_emit_kernel(
-    const unsigned long long* __restrict__ accepted, const int* __restrict__ accepted_count, int* kept_hist,
-    int max_corners, unsigned long long* __restrict__ spill, int spill_cap, int w, float* __restrict__ kps,
-    int kps_cap, int* __restrict__ kps_count) {
+__global__ void __launch_bounds__(RANK_THREADS) select_rank_emit_kernel(
+    const unsigned long long* __restrict__ accepted, const int* __restrict__ accepted_count,
+    const int* __restrict__ kept_hist, int max_corners, int w, float* __restrict__ kps, int kps_cap,
+    int* __restrict__ kps_count) {
     extern __shared__ __align__(16) unsigned long long s_keys[];
-    __shared__ int s_warp[SORT_THREADS / 32], s_bin, s_fill;
-    const int t = threadIdx.x;
+    __shared__ int s_warp[RANK_THREADS / 32], s_res[8], s_fill;
+    const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
     const int n = *accepted_count;
     const int k = min(min(max_corners, n), kps_cap);
-    // 1. the 16-bit value bin that holds the k-th strongest kept key; the histogram is handed
-    //    back zeroed for the next frame
-    const unsigned thr = (unsigned)suffix_threshold_bin<SORT_THREADS, 64>(kept_hist, k, s_warp, &s_bin);
-    {
-        int4* hp = reinterpret_cast<int4*>(kept_hist) + t * 16;
+    if (blockIdx.x == 0 && t == 0) *kps_count = k;
+    if (k == 0) return;
+    int m;
+    const unsigned thr = (unsigned)suffix_threshold_bin<RANK_THREADS, 64>(kept_hist, k, s_warp, s_res, &m);
+    const bool in_smem = m <= RANK_SMEM_KEYS;
+    if (t == 0) s_fill = 0;
+    __syncthreads();
+    if (in_smem) {
+        for (int base = 0; base < n; base += RANK_THREADS) {
+            const int i = base + t;
+            unsigned long long key = 0ull;
+            bool keep = false;
+            if (i < n) {
+                key = accepted[i];
+                keep = (unsigned)(key >> 48) >= thr;
+            }
+            const unsigned bal = __ballot_sync(0xffffffffu, keep);
+            if (bal) {
+                const int leader = __ffs(bal) - 1;
+                int b = 0;
+                if (lane == leader) b = atomicAdd(&s_fill, __popc(bal));
+                b = __shfl_sync(0xffffffffu, b, leader);
+                if (keep) s_keys[b + __popc(bal & ((1u << lane) - 1))] = key;
+            }
+        }
+        __syncthreads();
+    }
+    // this CTA's share of the accepted list; one warp per candidate key
+    const int per_cta = (n + gridDim.x - 1) / gridDim.x;
+    const int lo = blockIdx.x * per_cta, hi = min(lo + per_cta, n);
+    for (int i = lo + wid; i < hi; i += RANK_THREADS / 32) {
+        const unsigned long long key = accepted[i];
+        if ((unsigned)(key >> 48) < thr) continue;          // warp-uniform
+        int cnt = 0;
+        if (in_smem) {
+            for (int j = lane; j < m; j += 32) cnt += s_keys[j] > key ? 1 : 0;
+        } else {                                             // pathological value plateau: scan the global list
+            for (int j = lane; j < n; j += 32) cnt += accepted[j] > key ? 1 : 0;
+        }
 #pragma unroll
-        for (int q = 0; q < 16; q++) hp[q] = make_int4(0, 0, 0, 0);
-    }
-    // 2. gather the keys at or above that bin
-    if (t == 0) s_fill = 0;
-    __syncthreads();
-    // count first (cheap: the list is L2 resident) to choose shared memory or the global spill
-    int mine = 0;
-    for (int i = t; i < n; i += SORT_THREADS) mine += ((unsigned)(accepted[i] >> 48) >= thr) ? 1 : 0;
-    if (mine) atomicAdd(&s_fill, mine);
-    __syncthreads();
-    const int m = s_fill;
-    int P = 1;
-    while (P < m) P <<= 1;
-    unsigned long long* arr = (P <= SORT_SMEM_KEYS) ? s_keys : spill;
-    // the spill buffer holds next_pow2(cand_cap) keys (csrc/abi/capi.cu), so P always fits
-    __syncthreads();
-    if (t == 0) s_fill = 0;
-    __syncthreads();
-    for (int base = 0; base < n; base += SORT_THREADS) {
-        const int i = base + t;
-        unsigned long long key = 0ull;
-        bool keep = false;
-        if (i < n) {
-            key = accepted[i];
-            keep = (unsigned)(key >> 48) >= thr;
+        for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        if (lane == 0 && cnt < k) {
+            const int addr = (int)(key & 0xffffffffu);
+            const int y = addr / w;
+            kps[2 * cnt] = (float)(addr - y * w);
+            kps[2 * cnt + 1] = (float)y;
         }
-        const unsigned bal = __ballot_sync(0xffffffffu, keep);
-        if (bal) {
-            const int lane = t & 31, leader = __ffs(bal) - 1;
-            int b = 0;
-            if (lane == leader) b = atomicAdd(&s_fill, __popc(bal));
-            b = __shfl_sync(0xffffffffu, b, leader);
-            if (keep) arr[b + __popc(bal & ((1u << lane) - 1))] = key;
-        }
-    }
-    for (int i = m + t; i < P; i += SORT_THREADS) arr[i] = 0ull;   // zero keys sort last
-    __syncthreads();
-    // 3. sort descending on (value, address) and emit the first k as keypoints
-    bitonic_sort_desc(arr, P);
-    if (t == 0) *kps_count = k;
-    for (int i = t; i < k; i += SORT_THREADS) {
-        const int addr = (int)(arr[i] & 0xffffffffu);
-        const int y = addr / w;
-        kps[2 * i] = (float)(addr - y * w);
-        kps[2 * i + 1] = (float)y;
     }
 }
 
@@ -357,11 +388,12 @@ void launch_select(const unsigned long long* cand, const int* cand_count, int ca
                    int eig_pitch, uint8_t* state, int state_pitch, int w, int h, double min_distance,
                    int max_corners, SelectWorkspace ws, float* kps_out, int kps_cap, int* kps_count, int sm_count,
                    cudaStream_t s) {
-    cudaFuncSetAttribute(select_sort_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (int)(SORT_SMEM_KEYS * sizeof(unsigned long long)));   // per device, cheap
+    cudaFuncSetAttribute(select_rank_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)(RANK_SMEM_KEYS * sizeof(unsigned long long)));   // per device, cheap
     cudaMemsetAsync(ws.accepted_count, 0, sizeof(int), s);
     const bool limited = max_corners > 0;
     int* kept_hist = limited ? ws.kept_hist : nullptr;
+    if (limited) cudaMemsetAsync(ws.kept_hist, 0, sizeof(int) * 65536, s);
     // the unlimited path sorts the whole accepted[] buffer: unused slots must be zero (they sort last)
     if (!limited) cudaMemsetAsync(ws.accepted, 0, sizeof(unsigned long long) * (size_t)ws.cap, s);
     if (min_distance >= 1.0) {
@@ -386,9 +418,8 @@ void launch_select(const unsigned long long* cand, const int* cand_count, int ca
     }
     // keys: [63:32] ordered value, [31:0] address (< w*h); zero keys sort last
     if (limited) {
-        select_sort_emit_kernel<<<1, SORT_THREADS, SORT_SMEM_KEYS * sizeof(unsigned long long), s>>>(
-            ws.accepted, ws.accepted_count, ws.kept_hist, max_corners, ws.sorted, ws.sorted_cap, w, kps_out, kps_cap,
-            kps_count);
+        select_rank_emit_kernel<<<sm_count < 64 ? sm_count : 64, RANK_THREADS, RANK_SMEM_KEYS * sizeof(unsigned long long), s>>>(
+            ws.accepted, ws.accepted_count, ws.kept_hist, max_corners, w, kps_out, kps_cap, kps_count);
     } else {
         size_t temp = ws.cub_temp_bytes;
         cub::DeviceRadixSort::SortKeysDescending(ws.cub_temp, temp, ws.accepted, ws.sorted, ws.cap, 0, 64, s);

@@ -14,11 +14,15 @@
 // sequential chain of small problems, so launch and sync latency, not bandwidth, bound it.
 // Per-thread partial sums are float32; the cross-thread reduction is float64 (the reference's
 // own sums are order-nondeterministic under TBB; this sits inside that band).
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 #include "geom.cuh"
 #include "kernels.h"
 #include "track_kernels.h"
 #include "bvh.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace pc {
 
@@ -82,13 +86,21 @@ void launch_raycast_sources(const MeshView& mesh, const RaySource* srcs_dev, int
                                                                 x_out, valid, prim_out, uv_out, t_out, pos_out);
 }
 
-// ---- K11: dense LM on one CTA ------------------------------------------------------------
+// ---- K11: dense LM, the whole loop in one launch on a cluster of PNP_CLUSTER CTAs ---------------
+// The matches are striped over the cluster's threads; every reduction (cost, or the 45 + 9
+// normal-equation sums) goes warp shuffle -> CTA shared memory -> distributed shared memory: each
+// CTA publishes its partial, one cluster barrier, and every CTA adds the PNP_CLUSTER partials in
+// rank order.  All CTAs therefore hold bit-identical totals and run the (tiny) 9x9 solve and the
+// LM accept/reject logic redundantly: no second barrier, no global memory, no host round trip.
 constexpr int PNP_THREADS = 512;
+constexpr int PNP_CLUSTER = 8;       // portable cluster size
 constexpr int PNP_NACC = 45 + 9;     // lower triangle of JtJ + Jtr
 
 struct PnpShared {
     double red[32][PNP_NACC + 2];
+    double part[2][PNP_NACC + 2];    // this CTA's partial sums, double-buffered across reductions
     double total[PNP_NACC + 2];
+    int parity;
     float JtJ[81];
     float diag[9];
     float Jtr[9];
@@ -99,7 +111,8 @@ struct PnpShared {
 };
 
 __device__ __forceinline__ double block_reduce_many(PnpShared& sh, const float* vals, int n) {
-    // reduces vals[0..n) over the block into sh.total[0..n) (double)
+    // reduces vals[0..n) over the whole cluster into sh.total[0..n) (double, same bits in every CTA)
+    cg::cluster_group cluster = cg::this_cluster();
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     for (int k = 0; k < n; k++) {
         double v = (double)vals[k];
@@ -108,11 +121,20 @@ __device__ __forceinline__ double block_reduce_many(PnpShared& sh, const float* 
         if (lane == 0) sh.red[wid][k] = v;
     }
     __syncthreads();
+    const int par = sh.parity;
     if (threadIdx.x < n) {
         double s = 0.0;
         for (int w = 0; w < PNP_THREADS / 32; w++) s += sh.red[w][threadIdx.x];
+        sh.part[par][threadIdx.x] = s;
+    }
+    cluster.sync();                                  // partials of every CTA are visible
+    if (threadIdx.x < n) {
+        double s = 0.0;
+        for (unsigned r = 0; r < cluster.num_blocks(); r++)
+            s += *cluster.map_shared_rank(&sh.part[par][threadIdx.x], r);
         sh.total[threadIdx.x] = s;
     }
+    if (threadIdx.x == 0) sh.parity = par ^ 1;       // the next reduction publishes into the other buffer
     __syncthreads();
     return 0.0;
 }
@@ -131,7 +153,9 @@ __device__ float pnp_total_cost(PnpShared& sh, const pc_camera_state& cs, const 
                                 const float* x, const float* w, const uint8_t* valid, int m) {
     const Cam c = make_cam(cs);
     float acc[1] = {0.f};
-    for (int i = threadIdx.x; i < m; i += PNP_THREADS) {
+    const int gtid = cg::this_cluster().block_rank() * PNP_THREADS + threadIdx.x;
+    const int gthreads = cg::this_cluster().num_blocks() * PNP_THREADS;
+    for (int i = gtid; i < m; i += gthreads) {
         if (valid && !valid[i]) continue;
         const float wi = w ? w[i] : 1.f;
         if (wi == 0.f) continue;                               // lev_marq.h:333-336
@@ -153,24 +177,28 @@ __global__ void __launch_bounds__(PNP_THREADS, 1) pnp_lm_kernel(const float* __r
                                                                 PnpParams prm, pc_camera_state* cam_io,
                                                                 PnpResult* result) {
     __shared__ PnpShared sh;
-    __shared__ int s_count;
+    cg::cluster_group cluster = cg::this_cluster();
     const int tid = threadIdx.x;
+    const bool lead = cluster.block_rank() == 0 && tid == 0;   // the one thread that writes results
+    const int gtid = cluster.block_rank() * PNP_THREADS + tid;
+    const int gthreads = cluster.num_blocks() * PNP_THREADS;
+    if (tid == 0) sh.parity = 0;
+    __syncthreads();
     // number of usable matches (rays that hit)
-    if (tid == 0) s_count = 0;
+    {
+        float cnt[1] = {0.f};
+        for (int i = gtid; i < m; i += gthreads) cnt[0] += (!valid || valid[i]) ? 1.f : 0.f;
+        block_reduce_many(sh, cnt, 1);
+    }
+    const int n_valid = (int)sh.total[0];
     __syncthreads();
-    int cnt = 0;
-    for (int i = tid; i < m; i += PNP_THREADS) cnt += (!valid || valid[i]) ? 1 : 0;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-    if ((tid & 31) == 0 && cnt) atomicAdd(&s_count, cnt);
-    __syncthreads();
-    const int n_valid = s_count;
-    if (tid == 0) {
+    if (lead) {
         result->num_matches = n_valid;
         result->status = 0;
     }
     if (n_valid < 3) {                                         // tracker.cc:95-97 / solvers.cc:55
-        if (tid == 0) result->status = 1;
+        if (lead) result->status = 1;
+        cluster.sync();                                        // nobody leaves while a peer may still read its smem
         return;
     }
     // pnp_problem.h:33-34: intrinsics are only optimised with more than 3 points
@@ -192,7 +220,7 @@ __global__ void __launch_bounds__(PNP_THREADS, 1) pnp_lm_kernel(const float* __r
             float acc[PNP_NACC];
 #pragma unroll
             for (int k = 0; k < PNP_NACC; k++) acc[k] = 0.f;
-            for (int i = tid; i < m; i += PNP_THREADS) {
+            for (int i = gtid; i < m; i += gthreads) {
                 if (valid && !valid[i]) continue;
                 const float wi = w ? w[i] : 1.f;
                 if (wi == 0.f) continue;
@@ -354,7 +382,7 @@ __global__ void __launch_bounds__(PNP_THREADS, 1) pnp_lm_kernel(const float* __r
     float acc[1] = {0.f};
     if (prm.max_inlier_error > 0.f) {
         const float thr2 = prm.max_inlier_error * prm.max_inlier_error;
-        for (int i = tid; i < m; i += PNP_THREADS) {
+        for (int i = gtid; i < m; i += gthreads) {
             if (valid && !valid[i]) continue;
             float rx, ry;
             bool behind;
@@ -365,7 +393,7 @@ __global__ void __launch_bounds__(PNP_THREADS, 1) pnp_lm_kernel(const float* __r
         }
     }
     block_reduce_many(sh, acc, 1);
-    if (tid == 0) {
+    if (lead) {
         *cam_io = sh.cam;
         result->stats.iterations = it;
         result->stats.initial_cost = initial_cost;
@@ -376,11 +404,24 @@ __global__ void __launch_bounds__(PNP_THREADS, 1) pnp_lm_kernel(const float* __r
         result->stats.grad_norm = grad_norm;
         result->inlier_ratio = (float)sh.total[0] / (float)n_valid;
     }
+    cluster.sync();                                            // keep every CTA's shared memory alive until all have read it
 }
 
 void launch_pnp_lm(const float* X, const float* x, const float* w, const uint8_t* valid, int m, const PnpParams& prm,
                    pc_camera_state* cam_io, PnpResult* result, cudaStream_t s) {
-    pnp_lm_kernel<<<1, PNP_THREADS, 0, s>>>(X, x, w, valid, m, prm, cam_io, result);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(PNP_CLUSTER);
+    cfg.blockDim = dim3(PNP_THREADS);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = PNP_CLUSTER;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, pnp_lm_kernel, X, x, w, valid, m, prm, cam_io, result);
 }
 
 }  // namespace pc
