@@ -251,26 +251,23 @@ def main():
         m = idx % period
         return m if m < ring else period - m
 
-    # ---- Track (tracker.cc:36-213): forward PnP sweep fed by the flows as they are produced ----
-    # A second context owns the mesh and the PnP scratch so that its (host-synchronous) calls run
-    # on their own stream next to the analyzer's queued kernels.
-    trk = None
-    if track:
-        trk = capi.Context(device=local_rank, max_width=64, max_height=64, max_features=1024)
-        verts, tris = synth.plane_mesh(w, h, scale)
-        trk.mesh_set(verts, tris)
+    # ---- Track (tracker.cc:36-213): the forward PnP sweep, chained on the device behind the analyzer
+    # (pc_analyze_track_begin): each frame's ray cast + LM solve is queued right after its LK batch
+    # and reads the flow rows / source poses where they already are in HBM.
     bundle = capi.default_bundle()
     model = np.eye(4, dtype=np.float32)
+    if track:
+        verts, tris = synth.plane_mesh(w, h, scale)
+        ctx.mesh_set(verts, tris)
 
     class Sweep:
-        """State of one forward sweep: keypoints / tracked cameras of the last 9 frames."""
+        """Accumulates the tracked poses' statistics against the synthetic ground truth."""
 
         def __init__(self, ring: int):
             self.ring = ring
-            self.kps = {}
-            self.cams = {}
             self.tracked = 0
             self.matches = 0
+            self.iterations = 0
             self.max_t_err = 0.0
 
         def truth(self, idx: int):
@@ -278,27 +275,14 @@ def main():
             return capi.camera_state(K, Rs[i], ts[i])
 
         def consume(self, r, timed: bool):
-            """r: one analyze_pop result (views into pinned buffers, valid until the next pop)."""
-            f = r["frame_id"]
-            idx = f - (first - 8)
-            self.kps[f] = r["keypoints"].copy()
-            sources = []
-            for (a, b, rows, sidx, tgt, err) in r["pairs"]:
-                if b == f and a < f and rows and a in self.cams:
-                    sources.append((self.cams[a], self.kps[a], sidx, tgt))
-            if sources:
-                init = self.cams.get(f - 1) or self.truth(idx)
-                cam, st, inl, m = trk.track_frame(sources, model, init, bundle)
-                self.cams[f] = cam
-                if timed:
-                    self.tracked += 1
-                    self.matches += m
-                    i = image_of(idx, self.ring)
-                    self.max_t_err = max(self.max_t_err, float(np.abs(np.array(cam.t[:]) - ts[i]).max()))
-            else:
-                self.cams[f] = self.truth(idx)               # sweep start: known pose
-            for d in (self.kps, self.cams):
-                d.pop(f - 9, None)
+            if r["tracked"] != 1 or not timed:
+                return
+            idx = r["frame_id"] - (first - 8)
+            self.tracked += 1
+            self.matches += r["num_matches"]
+            self.iterations += r["stats"].iterations
+            i = image_of(idx, self.ring)
+            self.max_t_err = max(self.max_t_err, float(np.abs(np.array(r["camera"].t[:]) - ts[i]).max()))
 
     def run_steps(n_steps: int, start_frame_idx: int, mem_kind: int, base_ptr: int, ring: int, download: bool,
                   sweep=None, timed=False):
@@ -334,10 +318,12 @@ def main():
         torch.cuda.synchronize()
 
     def timed_leg(mem_kind: int, base_ptr: int, ring: int, download: bool):
-        download = download or track                         # the tracker consumes host flow rows
         sweep = Sweep(ring) if track else None
         ctx.analyze_begin(w, h, first - 8, 10 ** 6, gftt, flow)
         ctx.analyze_set_halo(8)
+        if track:                                            # the sweep starts from the shard's known pose:
+            ctx.analyze_track_begin(model, bundle)           # the frame before its first own frame
+            ctx.analyze_track_seed(first - 1, sweep.truth(7))
         idx = 0
         for _ in range(8):                                   # halo frames of the previous shard
             ctx.analyze_push(first - 8 + idx, base_ptr + image_of(idx, ring) * frame_bytes, stride, mem_kind)
@@ -350,17 +336,14 @@ def main():
         drain(download, sweep)
         ctx.timing_read(reset=True)
         ctx.timing_enable(True)
-        if trk:
-            trk.timing_read(reset=True)
-            trk.timing_enable(True)
-        launches0 = ctx.kernel_launches() + (trk.kernel_launches() if trk else 0)
+        launches0 = ctx.kernel_launches()
         sampler = ClockSampler(local_rank)
         barrier()
         sampler.start()
         ctx.mark(0)
         t0 = time.perf_counter()
         pairs, rows, idx = run_steps(args.steps, idx, mem_kind, base_ptr, ring, download, sweep, True)
-        p2, r2 = drain(download, sweep, True)                # the last track call is host-synchronous,
+        p2, r2 = drain(download, sweep, True)                # pops wait for each frame's rows and pose,
         ctx.mark(1)                                          # so mark 1 is recorded after all the work
         ctx.synchronize()
         barrier()
@@ -369,18 +352,14 @@ def main():
         dev_ms = ctx.elapsed_ms(0, 1)
         times = ctx.timing_read(reset=True)
         ctx.timing_enable(False)
-        if trk:
-            tt = trk.timing_read(reset=True)
-            trk.timing_enable(False)
-            for key, val in tt.items():
-                times[key] = times.get(key, 0) + val
-        launches = ctx.kernel_launches() + (trk.kernel_launches() if trk else 0) - launches0
+        launches = ctx.kernel_launches() - launches0
         ctx.analyze_end()
         out = dict(pairs=pairs + p2, rows=rows + r2, dev_ms=dev_ms, wall_s=wall, clocks=clocks, times=times,
                    launches=launches)
         if sweep is not None:
             out["track"] = {"frames_tracked": sweep.tracked,
                             "matches_per_frame": sweep.matches / max(sweep.tracked, 1),
+                            "lm_iterations_per_frame": sweep.iterations / max(sweep.tracked, 1),
                             "max_abs_translation_error": sweep.max_t_err}
         return out
 
@@ -481,8 +460,6 @@ def main():
     if rank == 0:
         print(json.dumps(line))
     ctx.device_free(dev_frames)
-    if trk:
-        trk.close()
     ctx.close()
 
 

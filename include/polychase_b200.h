@@ -186,6 +186,12 @@ typedef struct pc_frame_result {
     const float* keypoints;          /* num_keypoints x 2, valid until the next pop */
     int32_t num_pairs;
     pc_pair_rows pairs[8];
+    /* fused Analyze -> Track (pc_analyze_track_begin): this frame's pose */
+    int32_t tracked;                 /* 0 no pose, 1 solved on the device, 2 seeded (known) pose */
+    int32_t num_matches;             /* rays that hit the mesh (tracker.cc:64-92) */
+    float inlier_ratio;
+    pc_camera_state camera;
+    pc_bundle_stats stats;
 } pc_frame_result;
 
 #define PC_MEM_HOST 0
@@ -202,6 +208,17 @@ PC_API int pc_analyze_preset_keypoints(pc_ctx*, int32_t frame_id, const float* k
  * fetched (pointers NULL): results stay device resident. */
 PC_API int pc_analyze_pop(pc_ctx*, pc_frame_result* out, int download);
 PC_API int pc_analyze_pending(pc_ctx*);
+/* Fused Analyze -> Track: a forward TrackSequence (tracker.cc:133-213) chained on the device
+ * behind the analyzer.  Call after pc_analyze_begin and pc_mesh_set, before the first push.
+ * Every pushed non-halo frame that has flows from already posed earlier frames is solved
+ * (SolveFrame, tracker.cc:36-131: ray cast of the matched source keypoints + robust LM from the
+ * previous frame's pose) right after its LK batch, from the flow rows still resident in HBM --
+ * no host round trip; the result arrives with pc_analyze_pop.  Frames whose pose is known (the
+ * sweep's first frame -- TrackSequence seeds it from the scene's view matrix, tracker.cc:205-207
+ * -- or a shard's halo) are given with pc_analyze_track_seed before they are pushed. */
+PC_API int pc_analyze_track_begin(pc_ctx*, const float model[16], const pc_bundle_opts*,
+                                  int optimize_focal_length, int optimize_principal_point);
+PC_API int pc_analyze_track_seed(pc_ctx*, int32_t frame_id, const pc_camera_state* cam);
 /* Multi-GPU sharding: the first `halo_frames` frames pushed after
  * pc_analyze_begin are prepared and detected but emit no pair rows -- they are the previous
  * shard's last frames, needed only as partners of this shard's pairs. */

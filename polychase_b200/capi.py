@@ -75,7 +75,9 @@ class PairRows(C.Structure):
 
 class FrameResult(C.Structure):
     _fields_ = [("frame_id", C.c_int32), ("num_keypoints", C.c_int32), ("keypoints", C.POINTER(C.c_float)),
-                ("num_pairs", C.c_int32), ("pairs", PairRows * 8)]
+                ("num_pairs", C.c_int32), ("pairs", PairRows * 8),
+                ("tracked", C.c_int32), ("num_matches", C.c_int32), ("inlier_ratio", C.c_float),
+                ("camera", CameraState), ("stats", BundleStats)]
 
 
 class KernelTimes(C.Structure):
@@ -133,6 +135,8 @@ SIGNATURES = {
     "pc_analyze_pending": (C.c_int, [C.c_void_p]),
     "pc_analyze_end": (C.c_int, [C.c_void_p]),
     "pc_analyze_set_halo": (C.c_int, [C.c_void_p, C.c_int]),
+    "pc_analyze_track_begin": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(BundleOpts), C.c_int, C.c_int]),
+    "pc_analyze_track_seed": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(CameraState)]),
     "pc_mark": (C.c_int, [C.c_void_p, C.c_int]),
     "pc_elapsed_ms": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_float)]),
     "pc_synth_set_texture": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
@@ -369,7 +373,23 @@ class Context:
             else:
                 idx = tgt = err = None
             out["pairs"].append((p.image_id_from, p.image_id_to, p.rows, idx, tgt, err))
+        out["tracked"] = r.tracked
+        if r.tracked:
+            out["camera"] = CameraState.from_buffer_copy(r.camera)
+            out["num_matches"] = r.num_matches
+            out["inlier_ratio"] = float(r.inlier_ratio)
+            out["stats"] = BundleStats.from_buffer_copy(r.stats)
         return out
+
+    def analyze_track_begin(self, model: np.ndarray, opts: Optional[BundleOpts] = None, opt_f: bool = False,
+                            opt_pp: bool = False):
+        """Chains a forward TrackSequence behind the analyzer (call after analyze_begin + mesh_set)."""
+        model = np.ascontiguousarray(model, np.float32).reshape(16)
+        opts = opts or default_bundle()
+        self._chk(self.lib.pc_analyze_track_begin(self.h, _ptr(model), C.byref(opts), int(opt_f), int(opt_pp)))
+
+    def analyze_track_seed(self, frame_id: int, cam: CameraState):
+        self._chk(self.lib.pc_analyze_track_seed(self.h, frame_id, C.byref(cam)))
 
     def analyze_set_halo(self, n: int):
         self._chk(self.lib.pc_analyze_set_halo(self.h, n))

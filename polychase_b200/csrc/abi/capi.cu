@@ -233,6 +233,7 @@ pc_ctx::~pc_ctx() {
     if (compute) cudaStreamSynchronize(compute);
     if (h2d) cudaStreamSynchronize(h2d);
     if (d2h) cudaStreamSynchronize(d2h);
+    if (track && track->stream) cudaStreamSynchronize(track->stream);
     for (auto& s : slots) {
         if (s.level[0].data) cudaFree(s.level[0].data);
         cudaFree(s.kps); cudaFree(s.n_kps);
@@ -247,6 +248,8 @@ pc_ctx::~pc_ctx() {
         cudaFree(st.rgb_dev);
         for (int k = 0; k < 8; k++) { free_pair_out(st.dev[k], false); free_pair_out(st.host[k], true); }
         cudaFreeHost(st.kps_host); cudaFreeHost(st.counts_host);
+        cudaFree(st.trk_result_dev); cudaFreeHost(st.trk_result_host); cudaFreeHost(st.trk_cam_host);
+        if (st.tracked) cudaEventDestroy(st.tracked);
         if (st.uploaded) cudaEventDestroy(st.uploaded);
         if (st.gray_done) cudaEventDestroy(st.gray_done);
         if (st.computed) cudaEventDestroy(st.computed);
@@ -258,6 +261,7 @@ pc_ctx::~pc_ctx() {
     for (auto e : marks) if (e) cudaEventDestroy(e);
     if (join_a) cudaEventDestroy(join_a);
     if (join_b) cudaEventDestroy(join_b);
+    if (track) free_track_chain(track);
     if (mesh) free_mesh(mesh);
     if (ba) free_ba(ba);
     if (compute) cudaStreamDestroy(compute);
@@ -389,6 +393,7 @@ int pc_synchronize(pc_ctx* c) {
     PC_CUDA(c, cudaStreamSynchronize(c->h2d));
     PC_CUDA(c, cudaStreamSynchronize(c->compute));
     PC_CUDA(c, cudaStreamSynchronize(c->d2h));
+    if (c->track && c->track->stream) PC_CUDA(c, cudaStreamSynchronize(c->track->stream));
     return PC_OK;
 }
 
@@ -650,7 +655,8 @@ int pc_analyze_begin(pc_ctx* c, const pc_video_info* vi, const pc_gftt_opts* go,
     c->halo_frames = 0;
     c->pushed_count = 0;
     c->preset_kps.clear();
-    for (auto& st : c->stages) { st.busy = false; st.gray_pending = false; }
+    for (auto& st : c->stages) { st.busy = false; st.gray_pending = false; st.track_state = 0; }
+    if (c->track) c->track->on = false;
     c->analyzing = true;
     return PC_OK;
 }
@@ -684,6 +690,10 @@ int pc_mark(pc_ctx* c, int slot) {
     PC_CUDA(c, cudaEventRecord(c->join_b, c->d2h));
     PC_CUDA(c, cudaStreamWaitEvent(c->compute, c->join_a, 0));
     PC_CUDA(c, cudaStreamWaitEvent(c->compute, c->join_b, 0));
+    if (c->track && c->track->stream) {
+        PC_CUDA(c, cudaEventRecord(c->track->join, c->track->stream));
+        PC_CUDA(c, cudaStreamWaitEvent(c->compute, c->track->join, 0));
+    }
     PC_CUDA(c, cudaEventRecord(c->marks[slot], c->compute));
     return PC_OK;
 }
@@ -790,6 +800,8 @@ int pc_analyze_push_frame(pc_ctx* c, int32_t frame_id, const uint8_t* rgb, size_
         if (rc) return rc;
     }
     PC_CUDA(c, cudaEventRecord(st.computed, c->compute));
+    rc = track_chain_enqueue(c, st, frame_id, is_halo, batch.cap);     // fused Track (no-op unless enabled)
+    if (rc) return rc;
     // results -> pinned host, on the download stream
     PC_CUDA(c, cudaStreamWaitEvent(c->d2h, st.computed, 0));
     PC_CUDA(c, cudaMemcpyAsync(st.counts_host, f->n_kps, sizeof(int) * 3, cudaMemcpyDeviceToHost, c->d2h));
@@ -846,9 +858,10 @@ int pc_analyze_pop(pc_ctx* c, pc_frame_result* out, int download) {
             r.flow_errors = st.host[k].err;
         }
     }
+    rc = track_chain_collect(c, st, out);
     c->inflight.pop_front();
     st.busy = false;
-    return PC_OK;
+    return rc;
 }
 
 int pc_analyze_end(pc_ctx* c) {

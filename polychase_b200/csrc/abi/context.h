@@ -11,6 +11,7 @@
 
 #include "../../../include/polychase_b200.h"
 #include "../kernels/kernels.h"
+#include "../kernels/track_kernels.h"
 
 namespace pc {
 
@@ -54,6 +55,32 @@ struct Stage {                // one in-flight frame of the streaming analyzer
     cudaEvent_t uploaded = nullptr, gray_done = nullptr, computed = nullptr, downloaded = nullptr;
     bool busy = false;
     bool gray_pending = false;
+    // fused analyze -> track chain (track.cu): this frame's pose solve
+    int track_state = 0;              // 0 none, 1 solved on the device, 2 seeded (known pose)
+    PnpResult* trk_result_dev = nullptr;
+    PnpResult* trk_result_host = nullptr;        // pinned
+    pc_camera_state* trk_cam_host = nullptr;     // pinned
+    cudaEvent_t tracked = nullptr;
+};
+
+// Device-resident forward tracking sweep chained behind the analyzer (SolveFrame,
+// /root/reference/cpp/tracker.cc:36-131, called per frame by TrackCameraTrajectory :133-192).
+constexpr int kCamRing = 32;                     // >= 8 (largest skip) + pipeline depth
+struct TrackChain {
+    bool on = false;
+    float model[16];
+    pc_bundle_opts bo{};
+    int opt_f = 0, opt_pp = 0;
+    cudaStream_t stream = nullptr;               // high priority: the latency-bound chain goes first
+    cudaEvent_t join = nullptr;                  // pc_mark joins this stream into the compute stream
+    pc_camera_state* d_cams = nullptr;           // kCamRing slots, slot = frame_id mod kCamRing
+    int32_t cam_frame[kCamRing];                 // host: which frame's pose the slot holds
+    bool cam_known[kCamRing];
+    std::unordered_map<int32_t, pc_camera_state> seeds;   // known poses, uploaded when their frame is pushed
+    bool have_bounds = false;
+    Bounds bounds{};                             // solvers.cc:19-21, from the first seed's intrinsics
+    float* d_X = nullptr; float* d_x = nullptr; uint8_t* d_valid = nullptr;
+    size_t cap_rows = 0;
 };
 
 struct MeshData;   // track.cu
@@ -110,6 +137,7 @@ struct pc_ctx {
     // track / refine state
     pc::MeshData* mesh = nullptr;
     pc::BAData* ba = nullptr;
+    pc::TrackChain* track = nullptr;
 
     ~pc_ctx();
 };
@@ -141,6 +169,10 @@ FrameSlot* find_slot(pc_ctx* c, int32_t frame_id);
 PyramidView view_of(const FrameSlot& f);
 
 void free_mesh(MeshData*);
+void free_track_chain(TrackChain*);
+// fused chain hooks used by the streaming analyzer (capi.cu)
+int track_chain_enqueue(pc_ctx* c, Stage& st, int32_t frame_id, bool is_halo, int cap);
+int track_chain_collect(pc_ctx* c, Stage& st, pc_frame_result* out);
 void free_ba(BAData*);
 
 }  // namespace pc

@@ -36,7 +36,6 @@ struct MeshData {
 };
 
 MeshView mesh_view(const MeshData* m);
-bool invert4x4(const double m[16], double inv[16]);
 int validate_bundle_opts(pc_ctx* c, const pc_bundle_opts* o);
 
 }  // namespace pc

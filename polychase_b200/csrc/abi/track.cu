@@ -110,54 +110,6 @@ int ensure_match_capacity(pc_ctx* c, MeshData* m, size_t rows) {
     return PC_OK;
 }
 
-// inverse of a general 4x4 (row-major) in double; false if singular
-bool invert4x4(const double m[16], double inv[16]) {
-    double a[4][8];
-    for (int r = 0; r < 4; r++)
-        for (int c = 0; c < 4; c++) { a[r][c] = m[r * 4 + c]; a[r][4 + c] = r == c ? 1.0 : 0.0; }
-    for (int col = 0; col < 4; col++) {
-        int piv = col;
-        for (int r = col + 1; r < 4; r++)
-            if (fabs(a[r][col]) > fabs(a[piv][col])) piv = r;
-        if (a[piv][col] == 0.0) return false;
-        if (piv != col)
-            for (int k = 0; k < 8; k++) std::swap(a[piv][k], a[col][k]);
-        const double d = 1.0 / a[col][col];
-        for (int k = 0; k < 8; k++) a[col][k] *= d;
-        for (int r = 0; r < 4; r++)
-            if (r != col) {
-                const double f = a[r][col];
-                if (f != 0.0)
-                    for (int k = 0; k < 8; k++) a[r][k] -= f * a[col][k];
-            }
-    }
-    for (int r = 0; r < 4; r++)
-        for (int c = 0; c < 4; c++) inv[r * 4 + c] = a[r][4 + c];
-    return true;
-}
-
-// GetRayObjectSpace (ray_casting.h:53-63): mat = (view * model)^-1, origin = mat.col(3),
-// dir = mat[3x3] * Unproject(pos).  The reference inverts in float32 (Eigen general inverse);
-// here the inverse is formed in double and rounded once.
-bool make_ray_source(const pc_camera_state& cam, const float model[16], RaySource& s) {
-    const Cam c = make_cam(cam);
-    double view[16] = {c.R.m[0], c.R.m[1], c.R.m[2], c.t.x, c.R.m[3], c.R.m[4], c.R.m[5], c.t.y,
-                       c.R.m[6], c.R.m[7], c.R.m[8], c.t.z, 0, 0, 0, 1};
-    double vm[16], inv[16];
-    for (int r = 0; r < 4; r++)
-        for (int cc = 0; cc < 4; cc++) {
-            double acc = 0;
-            for (int k = 0; k < 4; k++) acc += view[r * 4 + k] * (double)model[k * 4 + cc];
-            vm[r * 4 + cc] = acc;
-        }
-    if (!invert4x4(vm, inv)) return false;
-    s.origin = V3{(float)inv[3], (float)inv[7], (float)inv[11]};
-    for (int r = 0; r < 3; r++)
-        for (int cc = 0; cc < 3; cc++) s.dir_mat.m[r * 3 + cc] = (float)inv[r * 4 + cc];
-    s.fx = c.fx; s.fy = c.fy; s.cx = c.cx; s.cy = c.cy; s.sgn = c.sgn;
-    return true;
-}
-
 PnpParams make_pnp_params(const pc_bundle_opts* o, float max_inlier_error, int opt_f, int opt_pp,
                           const pc_camera_state& cam) {
     PnpParams p;
@@ -180,6 +132,122 @@ int validate_bundle_opts(pc_ctx* c, const pc_bundle_opts* o) {
     PC_CHECK(c, o != nullptr, "bundle options are required");
     if (o->loss_type < 0 || o->loss_type > 2)
         return fail(c, PC_ERR_INVALID, "Unknown loss type: " + std::to_string(o->loss_type));   // solvers.cc:67-70
+    return PC_OK;
+}
+
+
+// ---- fused analyze -> track chain ------------------------------------------------------------
+// TrackCameraTrajectory (tracker.cc:133-192) walks the frames in order and SolveFrame (:36-131)
+// needs, for frame f, the flows a -> f of every already posed frame a plus the pose of f-1 as the
+// start.  In a forward sweep that is exactly what the streaming analyzer has just produced for
+// the frame it pushed, so the ray cast and the LM solve are queued on a second (high priority)
+// stream right behind the frame's LK batch: flow rows, source keypoints and source poses are all
+// read from HBM where earlier launches left them, and the solved pose lands in a device ring that
+// the next frames read.  The host only ever sees the results (pc_analyze_pop).
+void free_track_chain(TrackChain* t) {
+    if (!t) return;
+    cudaFree(t->d_cams); cudaFree(t->d_X); cudaFree(t->d_x); cudaFree(t->d_valid);
+    if (t->join) cudaEventDestroy(t->join);
+    if (t->stream) cudaStreamDestroy(t->stream);
+    delete t;
+}
+
+static inline int cam_slot(int32_t frame_id) { return ((frame_id % kCamRing) + kCamRing) % kCamRing; }
+
+static bool chain_knows(const TrackChain* t, int32_t frame_id) {
+    const int s = cam_slot(frame_id);
+    return t->cam_known[s] && t->cam_frame[s] == frame_id;
+}
+
+int track_chain_enqueue(pc_ctx* c, Stage& st, int32_t frame_id, bool is_halo, int cap) {
+    st.track_state = 0;
+    TrackChain* t = c->track;
+    if (!t || !t->on) return PC_OK;
+    const int slot = cam_slot(frame_id);
+    auto seed = t->seeds.find(frame_id);
+    if (seed != t->seeds.end()) {                 // known pose (TrackSequence's frame_from, tracker.cc:205-207)
+        *st.trk_cam_host = seed->second;
+        t->seeds.erase(seed);
+        PC_CUDA(c, cudaMemcpyAsync(t->d_cams + slot, st.trk_cam_host, sizeof(pc_camera_state), cudaMemcpyHostToDevice,
+                                   t->stream));
+        PC_CUDA(c, cudaEventRecord(st.tracked, t->stream));
+        t->cam_frame[slot] = frame_id;
+        t->cam_known[slot] = true;
+        st.track_state = 2;
+        return PC_OK;
+    }
+    t->cam_frame[slot] = frame_id;
+    t->cam_known[slot] = false;
+    if (is_halo) return PC_OK;
+    // sources: the pairs (a -> f) of this stage whose source frame is posed, ascending a like
+    // FindOpticalFlowsToImage returns them
+    MeshData* m = c->mesh;
+    ResidentSources rs{};
+    rs.cap = cap;
+    memcpy(rs.model, t->model, sizeof(rs.model));
+    int32_t best_init = INT32_MIN;
+    for (int k = st.num_pairs - 1; k >= 0; k--) {
+        if (st.to[k] != frame_id || st.from[k] >= frame_id || !chain_knows(t, st.from[k])) continue;
+        const FrameSlot* a = find_slot(c, st.from[k]);
+        if (!a) continue;
+        ResidentSource& s = rs.s[rs.nsrc++];
+        s.cam = t->d_cams + cam_slot(st.from[k]);
+        s.keypoints = a->kps;
+        s.indices = st.dev[k].idx;
+        s.targets = st.dev[k].tgt;
+        s.rows = st.dev[k].count;
+        best_init = std::max(best_init, st.from[k]);
+    }
+    if (rs.nsrc == 0) return PC_OK;               // nothing posed to track from: the frame stays unposed
+    const size_t rows = (size_t)rs.nsrc * cap;
+    if (t->cap_rows < rows) {
+        PC_CUDA(c, cudaStreamSynchronize(t->stream));
+        cudaFree(t->d_X); cudaFree(t->d_x); cudaFree(t->d_valid);
+        t->d_X = t->d_x = nullptr; t->d_valid = nullptr; t->cap_rows = 0;
+        const size_t want = (size_t)4 * std::max(cap, c->lim.max_features);
+        PC_CUDA(c, cudaMalloc(&t->d_X, sizeof(float) * 3 * want));
+        PC_CUDA(c, cudaMalloc(&t->d_x, sizeof(float) * 2 * want));
+        PC_CUDA(c, cudaMalloc(&t->d_valid, want));
+        t->cap_rows = want;
+    }
+    PC_CUDA(c, cudaStreamWaitEvent(t->stream, st.computed, 0));
+    span_begin(c, KF_RAYCAST, t->stream);
+    launch_raycast_resident(mesh_view(m), rs, t->d_X, t->d_x, t->d_valid, t->stream);
+    span_end(c, t->stream);
+    // the start of the solve is the previous frame's pose (tracker.cc:112-119)
+    PnpParams prm = make_pnp_params(&t->bo, 12.0f /* tracker.cc:123 */, t->opt_f, t->opt_pp, pc_camera_state{});
+    prm.bounds = t->bounds;
+    span_begin(c, KF_PNP, t->stream);
+    launch_pnp_lm(t->d_X, t->d_x, nullptr, t->d_valid, (int)rows, prm, t->d_cams + cam_slot(best_init),
+                  t->d_cams + slot, st.trk_result_dev, t->stream);
+    span_end(c, t->stream);
+    int rc = check_launch(c, "track chain", 2);
+    if (rc) return rc;
+    PC_CUDA(c, cudaMemcpyAsync(st.trk_result_host, st.trk_result_dev, sizeof(PnpResult), cudaMemcpyDeviceToHost, t->stream));
+    PC_CUDA(c, cudaMemcpyAsync(st.trk_cam_host, t->d_cams + slot, sizeof(pc_camera_state), cudaMemcpyDeviceToHost, t->stream));
+    PC_CUDA(c, cudaEventRecord(st.tracked, t->stream));
+    t->cam_known[slot] = true;
+    st.track_state = 1;
+    return PC_OK;
+}
+
+int track_chain_collect(pc_ctx* c, Stage& st, pc_frame_result* out) {
+    out->tracked = 0;
+    if (st.track_state == 0) return PC_OK;
+    PC_CUDA(c, cudaEventSynchronize(st.tracked));
+    out->tracked = st.track_state;
+    out->camera = *st.trk_cam_host;
+    if (st.track_state == 2) return PC_OK;
+    const PnpResult& r = *st.trk_result_host;
+    out->num_matches = r.num_matches;
+    if (r.status == 1) {                          // tracker.cc:160-166
+        out->tracked = 0;
+        if (c->track) c->track->cam_known[cam_slot(st.frame_id)] = false;
+        return fail(c, PC_ERR_NOT_ENOUGH_FEATURES,
+                    "Could not track to frame: " + std::to_string(st.frame_id) + ". Not enough features.");
+    }
+    out->inlier_ratio = r.inlier_ratio;
+    out->stats = r.stats;
     return PC_OK;
 }
 
@@ -302,7 +370,7 @@ static int run_pnp(pc_ctx* c, MeshData* m, const float* dX, const float* dx, con
     const PnpParams prm = make_pnp_params(bo, max_inlier_error, opt_f, opt_pp, *cam);
     PC_CUDA(c, cudaMemcpyAsync(m->d_cam, cam, sizeof(*cam), cudaMemcpyHostToDevice, st));
     span_begin(c, KF_PNP, st);
-    launch_pnp_lm(dX, dx, dw, dvalid, rows, prm, m->d_cam, m->d_result, st);
+    launch_pnp_lm(dX, dx, dw, dvalid, rows, prm, m->d_cam, m->d_cam, m->d_result, st);
     span_end(c, st);
     int rc = check_launch(c, "pnp", 1);
     if (rc) return rc;
@@ -405,6 +473,57 @@ int pc_track_frame(pc_ctx* c, const pc_match_source* srcs, int nsrc, const float
                  opt_pp, &cam, stats, inlier_ratio, num_matches);
     if (rc) return rc;
     *out = cam;
+    return PC_OK;
+}
+
+int pc_analyze_track_begin(pc_ctx* c, const float model[16], const pc_bundle_opts* bo, int opt_f, int opt_pp) {
+    PC_CUDA(c, cudaSetDevice(c->device));
+    if (!c->analyzing) return fail(c, PC_ERR_STATE, "no analyze pass is open");
+    PC_CHECK(c, !c->any_pushed, "start the track chain before the first push");
+    int rc = validate_bundle_opts(c, bo);
+    if (rc) return rc;
+    PC_CHECK(c, model != nullptr, "model matrix is required");
+    if (!c->mesh || !c->mesh->d_nodes) return fail(c, PC_ERR_STATE, "no mesh set");
+    if (!c->track) {
+        TrackChain* t = new TrackChain();
+        c->track = t;
+        int lo = 0, hi = 0;
+        PC_CUDA(c, cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        PC_CUDA(c, cudaStreamCreateWithPriority(&t->stream, cudaStreamNonBlocking, hi));
+        PC_CUDA(c, cudaEventCreateWithFlags(&t->join, cudaEventDisableTiming));
+        PC_CUDA(c, cudaMalloc(&t->d_cams, sizeof(pc_camera_state) * kCamRing));
+    }
+    TrackChain* t = c->track;
+    memcpy(t->model, model, sizeof(t->model));
+    t->bo = *bo;
+    t->opt_f = opt_f;
+    t->opt_pp = opt_pp;
+    t->seeds.clear();
+    t->have_bounds = false;
+    for (int i = 0; i < kCamRing; i++) { t->cam_known[i] = false; t->cam_frame[i] = 0; }
+    for (auto& st : c->stages) {
+        st.track_state = 0;
+        if (st.tracked) continue;
+        PC_CUDA(c, cudaMalloc(&st.trk_result_dev, sizeof(PnpResult)));
+        PC_CUDA(c, cudaMallocHost(&st.trk_result_host, sizeof(PnpResult)));
+        PC_CUDA(c, cudaMallocHost(&st.trk_cam_host, sizeof(pc_camera_state)));
+        PC_CUDA(c, cudaEventCreateWithFlags(&st.tracked, cudaEventDisableTiming));
+    }
+    t->on = true;
+    return PC_OK;
+}
+
+int pc_analyze_track_seed(pc_ctx* c, int32_t frame_id, const pc_camera_state* cam) {
+    TrackChain* t = c->track;
+    if (!c->analyzing || !t || !t->on) return fail(c, PC_ERR_STATE, "no track chain is open");
+    PC_CHECK(c, cam != nullptr, "camera state is required");
+    PC_CHECK(c, !c->any_pushed || frame_id > c->last_pushed, "seed a frame before it is pushed");
+    if (!t->have_bounds) {
+        t->bounds = get_bounds(*cam);
+        t->have_bounds = true;
+    }
+    t->seeds[frame_id] = *cam;
+    t->seeds[frame_id].filled = 1.f;
     return PC_OK;
 }
 

@@ -35,6 +35,71 @@ struct RaySource {
     int rows;
 };
 
+// inverse of a general 4x4 (row-major) in double, Gauss-Jordan with partial pivoting; false if
+// singular
+PC_HD bool invert4x4(const double m[16], double inv[16]) {
+    double a[4][8];
+    for (int r = 0; r < 4; r++)
+        for (int c = 0; c < 4; c++) { a[r][c] = m[r * 4 + c]; a[r][4 + c] = r == c ? 1.0 : 0.0; }
+    for (int col = 0; col < 4; col++) {
+        int piv = col;
+        for (int r = col + 1; r < 4; r++)
+            if (fabs(a[r][col]) > fabs(a[piv][col])) piv = r;
+        if (a[piv][col] == 0.0) return false;
+        if (piv != col)
+            for (int k = 0; k < 8; k++) { const double t = a[piv][k]; a[piv][k] = a[col][k]; a[col][k] = t; }
+        const double d = 1.0 / a[col][col];
+        for (int k = 0; k < 8; k++) a[col][k] *= d;
+        for (int r = 0; r < 4; r++)
+            if (r != col) {
+                const double f = a[r][col];
+                if (f != 0.0)
+                    for (int k = 0; k < 8; k++) a[r][k] -= f * a[col][k];
+            }
+    }
+    for (int r = 0; r < 4; r++)
+        for (int c = 0; c < 4; c++) inv[r * 4 + c] = a[r][4 + c];
+    return true;
+}
+
+// GetRayObjectSpace (ray_casting.h:53-63): mat = (view * model)^-1, origin = mat.col(3),
+// dir = mat[3x3] * Unproject(pos).  The reference inverts in float32 (Eigen general inverse);
+// here the inverse is formed in double and rounded once.  Fills origin / dir_mat / intrinsics.
+PC_HD bool make_ray_source(const pc_camera_state& cam, const float model[16], RaySource& s) {
+    const Cam c = make_cam(cam);
+    double view[16] = {c.R.m[0], c.R.m[1], c.R.m[2], c.t.x, c.R.m[3], c.R.m[4], c.R.m[5], c.t.y,
+                       c.R.m[6], c.R.m[7], c.R.m[8], c.t.z, 0, 0, 0, 1};
+    double vm[16], inv[16];
+    for (int r = 0; r < 4; r++)
+        for (int cc = 0; cc < 4; cc++) {
+            double acc = 0;
+            for (int k = 0; k < 4; k++) acc += view[r * 4 + k] * (double)model[k * 4 + cc];
+            vm[r * 4 + cc] = acc;
+        }
+    if (!invert4x4(vm, inv)) return false;
+    s.origin = V3{(float)inv[3], (float)inv[7], (float)inv[11]};
+    for (int r = 0; r < 3; r++)
+        for (int cc = 0; cc < 3; cc++) s.dir_mat.m[r * 3 + cc] = (float)inv[r * 4 + cc];
+    s.fx = c.fx; s.fy = c.fy; s.cx = c.cx; s.cy = c.cy; s.sgn = c.sgn;
+    return true;
+}
+
+// A source of the device-resident tracking chain: everything, including the row count and the
+// source camera, is read from device memory when the kernel runs.
+struct ResidentSource {
+    const pc_camera_state* cam;  // device: pose of the source frame (written by an earlier PnP launch)
+    const float* keypoints;      // device: source frame keypoints
+    const uint32_t* indices;     // device: compacted flow rows (keypoint index)
+    const float* targets;        // device: compacted flow rows (target position)
+    const int* rows;             // device: number of rows
+};
+struct ResidentSources {
+    ResidentSource s[8];
+    int nsrc;
+    int cap;                     // rows reserved per source in the output arrays
+    float model[16];
+};
+
 struct PnpParams {
     unsigned long long max_iterations;
     int loss_type;
@@ -55,7 +120,15 @@ void launch_raycast_sources(const MeshView& mesh, const RaySource* srcs_dev, int
                             const float model[16], float* X_out, float* x_out, uint8_t* valid, uint32_t* prim_out,
                             float* uv_out, float* t_out, float* pos_out, cudaStream_t s);
 
+// cam_in / cam_out / result are device pointers (cam_in may equal cam_out); nothing is read
+// back, so launches chain on a stream without host round trips.
+// Device-resident variant of K10 for the fused analyze->track chain: output row of (source s, row j)
+// is s * cap + j; rows beyond a source's count are marked invalid.
+void launch_raycast_resident(const MeshView& mesh, const ResidentSources& srcs, float* X_out, float* x_out,
+                             uint8_t* valid, cudaStream_t s);
+
 void launch_pnp_lm(const float* X, const float* x, const float* w, const uint8_t* valid, int m, const PnpParams& prm,
-                   pc_camera_state* cam_io, PnpResult* result, cudaStream_t s);
+                   const pc_camera_state* cam_in, pc_camera_state* cam_out, PnpResult* result, cudaStream_t s);
+int pnp_cluster_size();
 
 }  // namespace pc

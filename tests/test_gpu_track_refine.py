@@ -134,6 +134,69 @@ def test_track_sequence_matches_oracle(ctx_small, scene):
     assert dq < 2e-3 and dt < 2e-3
 
 
+@pytest.mark.parametrize("opt_f", [False, True])
+def test_fused_analyze_track_chain_matches_oracle(ctx_small, scene, opt_f):
+    """pc_analyze_track_begin: the forward sweep chained on the device behind the analyzer gives the
+    oracle's TrackSequence poses (tracker.cc:133-213) and the same analyze rows as the plain pass."""
+    from polychase_b200 import capi
+    clip, kps, flows, NF = scene["clip"], scene["kps"], scene["flows"], scene["NF"]
+    model = np.eye(4, dtype=F)
+    opts = opnp.BundleOptions(loss_type=opnp.CAUCHY)
+    start = H.oracle_cam(clip, 0)
+    want = otrack.track_sequence(kps, flows, 0, NF - 1, start, model, scene["verts"], scene["tris"], None, opts,
+                                 opt_f, False)
+    ctx_small.mesh_set(scene["verts"], scene["tris"])
+    ctx_small.analyze_begin(clip.width, clip.height, 0, NF, capi.default_gftt(max_corners=250))
+    ctx_small.analyze_track_begin(model, capi.default_bundle(loss_type=2), opt_f, False)
+    ctx_small.analyze_track_seed(0, H.to_abi(start))
+    got = {}
+
+    def take(r):
+        got[r["frame_id"]] = r
+        assert np.array_equal(r["keypoints"], kps[r["frame_id"]])
+        for (a, b, rows, idx, tgt, err) in r["pairs"]:
+            assert np.array_equal(idx, flows[(a, b)][0]) and np.array_equal(tgt, flows[(a, b)][1])
+
+    for k in range(NF):
+        ctx_small.analyze_push(k, clip.rgb(k))
+        if ctx_small.analyze_pending() >= 3:
+            take(ctx_small.analyze_pop())
+    while ctx_small.analyze_pending():
+        take(ctx_small.analyze_pop())
+    ctx_small.analyze_end()
+    assert got[0]["tracked"] == 2
+    for f in range(1, NF):
+        r = got[f]
+        assert r["tracked"] == 1
+        ocam, ost, oinl, om = want[f]
+        assert abs(r["num_matches"] - om) <= max(2, 0.002 * om)
+        g = H.from_abi(r["camera"])
+        dq, dt = H.pose_close(ocam, g)
+        assert dq < RTOL and dt < RTOL, (f, dq, dt)
+        assert abs(r["inlier_ratio"] - oinl) < 5e-3
+        assert abs(g.intrinsics.fy - ocam.intrinsics.fy) <= RTOL * abs(ocam.intrinsics.fy)
+
+
+def test_fused_chain_not_enough_features(ctx_small, scene):
+    """A frame whose rays all miss the mesh raises the reference's error (tracker.cc:160-166) at pop."""
+    from polychase_b200 import capi
+    clip, NF = scene["clip"], 3
+    far = scene["verts"].copy()
+    far[:, 0] += 1e4                                  # mesh out of view: every ray misses
+    ctx_small.mesh_set(far, scene["tris"])
+    ctx_small.analyze_begin(clip.width, clip.height, 0, NF, capi.default_gftt(max_corners=250))
+    ctx_small.analyze_track_begin(np.eye(4, dtype=F), capi.default_bundle())
+    ctx_small.analyze_track_seed(0, H.to_abi(H.oracle_cam(clip, 0)))
+    ctx_small.analyze_push(0, clip.rgb(0))
+    ctx_small.analyze_push(1, clip.rgb(1))
+    assert ctx_small.analyze_pop()["tracked"] == 2
+    with pytest.raises(capi.PcError) as e:
+        ctx_small.analyze_pop()
+    assert e.value.code == -7 and "Could not track to frame: 1" in str(e.value)
+    ctx_small.analyze_end()
+    ctx_small.mesh_set(scene["verts"], scene["tris"])
+
+
 def test_track_not_enough_features(ctx_small, scene):
     from polychase_b200 import capi
     ctx_small.mesh_set(scene["verts"], scene["tris"])
