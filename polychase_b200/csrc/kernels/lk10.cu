@@ -164,6 +164,138 @@ __device__ __forceinline__ void template_pass(const LevelRef& A, int ipx, int ip
     }
 }
 
+// ---- interior variants: aligned 32-bit loads + funnel shifts instead of byte gathers -----------
+// A lane's two column sets are 4 apart (SIMD chains: columns c and c+4) or adjacent (tail chain:
+// columns 8 and 9), so everything it needs from one source row lies in the 12 bytes that start at
+// the 4-byte boundary below its first byte: three aligned word loads off ONE row pointer
+// (immediate offsets 0/4/8) replace eight (template) or four (window) byte loads with their own
+// 64-bit addresses.  `step` is 8 * (first byte & 3); `simd` selects the column-set distance.
+// Frame levels are padded (pitch multiple of 128, slack after the last level), so the words may
+// run past the bytes actually used.
+__device__ __forceinline__ void load_row_words(const uint8_t* rowp, uint32_t& w0, uint32_t& w1, uint32_t& w2) {
+    const uint32_t* q = reinterpret_cast<const uint32_t*>(rowp);
+    w0 = __ldg(q); w1 = __ldg(q + 1); w2 = __ldg(q + 2);
+}
+
+__device__ __forceinline__ void template_pass_fast(const LevelRef& A, int ipx, int ipy, int xa, int simd, int w00,
+                                                   int w01, int w10, int w11, int (&Ival)[20], int (&Ix)[20],
+                                                   int (&Iy)[20], float& a11, float& a12, float& a22) {
+    const int X0 = ipx + xa - 1;                      // first byte of column set 0 (taps X-1 .. X+2)
+    const uint8_t* rowp = A.img + (size_t)(ipy - 1) * A.pitch + (X0 & ~3);
+    const int step = (X0 & 3) * 8;
+    const int step2 = simd ? 0 : 8;                   // tail: set 1 starts one byte after set 0
+    const uint32_t wa = pack_weights(w00, w01), wb = pack_weights(w10, w11);
+    uint32_t E[2][3] = {}, O[2][3] = {};
+    int ival_top[2] = {0, 0};
+    int tx[2] = {0, 0}, ty[2] = {0, 0};
+    a11 = 0.f; a12 = 0.f; a22 = 0.f;
+#pragma unroll
+    for (int rr = 0; rr < WIN + 3; rr++) {            // source rows ipy-1 .. ipy+11
+        uint32_t w0, w1, w2;
+        load_row_words(rowp, w0, w1, w2);
+        rowp += A.pitch;
+        uint32_t Q[2];
+        Q[0] = __funnelshift_r(w0, w1, step);         // bytes g0 g1 g2 g3 of set 0
+        const uint32_t N = __funnelshift_r(w1, w2, step);
+        Q[1] = __funnelshift_r(simd ? N : Q[0], N, step2);
+        uint32_t P[2];
+#pragma unroll
+        for (int s = 0; s < 2; s++) {
+            E[s][0] = E[s][1]; E[s][1] = E[s][2]; E[s][2] = Q[s] & 0x00ff00ffu;          // g0 | g2 << 16
+            O[s][0] = O[s][1]; O[s][1] = O[s][2]; O[s][2] = (Q[s] >> 8) & 0x00ff00ffu;   // g1 | g3 << 16
+            P[s] = Q[s] >> 8;                                                             // g1 | g2 << 8 (dp2a.lo)
+        }
+        if (rr >= 2) {
+            const int y = rr - 2;
+            if (y < WIN) {
+#pragma unroll
+                for (int s = 0; s < 2; s++) Ival[2 * y + s] = dp2a_su(wb, P[s], ival_top[s]) >> (W_BITS - 5);
+            }
+        }
+        if (rr >= 1 && rr <= WIN) {
+#pragma unroll
+            for (int s = 0; s < 2; s++) ival_top[s] = dp2a_su(wa, P[s], 1 << (W_BITS - 5 - 1));
+        }
+        if (rr >= 2) {
+            const int t = rr - 2;
+#pragma unroll
+            for (int s = 0; s < 2; s++) {
+                const uint32_t VE = 3u * (E[s][0] + E[s][2]) + 10u * E[s][1];
+                const uint32_t VO = 3u * (O[s][0] + O[s][2]) + 10u * O[s][1];
+                const uint32_t UE = E[s][2] + 0x01000100u - E[s][0];
+                const uint32_t UO = O[s][2] + 0x01000100u - O[s][0];
+                const int dx0 = (int)(VE >> 16) - (int)(VE & 0xffffu);
+                const int dx1 = (int)(VO >> 16) - (int)(VO & 0xffffu);
+                const int u0 = UE & 0xffffu, u2 = UE >> 16, u1 = UO & 0xffffu, u3 = UO >> 16;
+                const int dy0 = 3 * (u0 + u2) + 10 * u1 - 4096;
+                const int dy1 = 3 * (u1 + u3) + 10 * u2 - 4096;
+                if (t >= 1) {
+                    const int y = t - 1;
+                    Ix[2 * y + s] = (tx[s] + dx0 * w10 + dx1 * w11) >> W_BITS;
+                    Iy[2 * y + s] = (ty[s] + dy0 * w10 + dy1 * w11) >> W_BITS;
+                }
+                if (t < WIN) {
+                    tx[s] = dx0 * w00 + dx1 * w01 + (1 << (W_BITS - 1));
+                    ty[s] = dy0 * w00 + dy1 * w01 + (1 << (W_BITS - 1));
+                }
+            }
+            if (t >= 1) {
+                const int y = t - 1;
+#pragma unroll
+                for (int s = 0; s < 2; s++) {
+                    const int ix = Ix[2 * y + s], iy = Iy[2 * y + s];
+                    a11 = __fadd_rn(a11, (float)(ix * ix));
+                    a12 = __fadd_rn(a12, (float)(ix * iy));
+                    a22 = __fadd_rn(a22, (float)(iy * iy));
+                }
+            }
+        }
+    }
+}
+
+template <bool ERR>
+__device__ __forceinline__ void window_pass_fast(const LevelRef& B, int inx, int iny, int xa, int simd, int w00,
+                                                 int w01, int w10, int w11, const int (&Ival)[20],
+                                                 const int (&Ix)[20], const int (&Iy)[20], float& bx, float& by,
+                                                 int& esum) {
+    const int X0 = inx + xa;
+    const uint8_t* rowp = B.img + (size_t)iny * B.pitch + (X0 & ~3);
+    const int step = (X0 & 3) * 8;
+    const int step2 = simd ? step : 8;
+    const uint32_t wa = pack_weights(w00, w01), wb = pack_weights(w10, w11);
+    int top[2] = {0, 0};
+    bx = 0.f; by = 0.f; esum = 0;
+#pragma unroll
+    for (int rr = 0; rr <= WIN; rr++) {               // target rows iny .. iny+10
+        uint32_t w0, w1, w2;
+        load_row_words(rowp, w0, w1, w2);
+        rowp += B.pitch;
+        uint32_t P[2];
+        P[0] = __funnelshift_r(w0, w1, step);         // bytes X0, X0+1 in the low half (dp2a.lo)
+        P[1] = __funnelshift_r(simd ? w1 : P[0], w2, step2);
+        if (rr >= 1) {
+            const int y = rr - 1;
+            const int d0 = (dp2a_su(wb, P[0], top[0]) >> (W_BITS - 5)) - Ival[2 * y];
+            const int d1 = (dp2a_su(wb, P[1], top[1]) >> (W_BITS - 5)) - Ival[2 * y + 1];
+            if (ERR) {
+                esum += abs(d0) + abs(d1);
+            } else {
+                // SIMD chains add the two columns' integer products before converting (pmaddwd);
+                // the tail chain converts and adds them one by one (x + (+0) == x for the others)
+                const int d1s = simd ? d1 : 0, d1t = simd ? 0 : d1;
+                bx = __fadd_rn(bx, (float)(d0 * Ix[2 * y] + d1s * Ix[2 * y + 1]));
+                by = __fadd_rn(by, (float)(d0 * Iy[2 * y] + d1s * Iy[2 * y + 1]));
+                bx = __fadd_rn(bx, (float)(d1t * Ix[2 * y + 1]));
+                by = __fadd_rn(by, (float)(d1t * Iy[2 * y + 1]));
+            }
+        }
+        if (rr < WIN) {
+            top[0] = dp2a_su(wa, P[0], 1 << (W_BITS - 5 - 1));
+            top[1] = dp2a_su(wa, P[1], 1 << (W_BITS - 5 - 1));
+        }
+    }
+}
+
 // ---- one pass over the target window: b1/b2 chain terms (ERR = false) or the L1 error -------
 template <bool BORDER, bool ERR>
 __device__ __forceinline__ void window_pass(const LevelRef& B, int inx, int iny, int xa, int xb, int w00, int w01,
@@ -213,7 +345,9 @@ __device__ __forceinline__ void window_pass(const LevelRef& B, int inx, int iny,
 }
 
 __global__ void __launch_bounds__(LK_WARPS * 32, 4) lk10_kernel(LKBatch batch, LKParams prm) {
-    const LKPair& pr = batch.pair[blockIdx.y];
+    // large skips take several times more iterations (slow pairs are appended last): schedule
+    // them first so the launch does not end on a tail of long blocks
+    const LKPair& pr = batch.pair[gridDim.y - 1 - blockIdx.y];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int grp = lane / PENTAD, role = lane - grp * PENTAD;
     const int base = grp < PTS_PER_WARP ? grp * PENTAD : 0;       // first lane of this pentad (shuffle source)
@@ -261,7 +395,7 @@ __global__ void __launch_bounds__(LK_WARPS * 32, 4) lk10_kernel(LKBatch batch, L
             const bool any_border = __any_sync(FULL, act && !t_inside);
             if (act) {
                 if (any_border) template_pass<true>(A, ipx, ipy, xa, xb, w00, w01, w10, w11, Ival, Ix, Iy, a11, a12, a22);
-                else template_pass<false>(A, ipx, ipy, xa, xb, w00, w01, w10, w11, Ival, Ix, Iy, a11, a12, a22);
+                else template_pass_fast(A, ipx, ipy, xa, simd_flag, w00, w01, w10, w11, Ival, Ix, Iy, a11, a12, a22);
             }
             __syncwarp();
         }
@@ -298,7 +432,7 @@ __global__ void __launch_bounds__(LK_WARPS * 32, 4) lk10_kernel(LKBatch batch, L
                 if (any_border)
                     window_pass<true, false>(B, inx, iny, xa, xb, w00, w01, w10, w11, Ival, Ix, Iy, simd_flag, tail_flag, bx, by, unused);
                 else
-                    window_pass<false, false>(B, inx, iny, xa, xb, w00, w01, w10, w11, Ival, Ix, Iy, simd_flag, tail_flag, bx, by, unused);
+                    window_pass_fast<false>(B, inx, iny, xa, simd_flag, w00, w01, w10, w11, Ival, Ix, Iy, bx, by, unused);
             }
             __syncwarp();
             const float b1 = __fmul_rn(pentad_total(bx, base), FLT_SCALE);
@@ -336,7 +470,7 @@ __global__ void __launch_bounds__(LK_WARPS * 32, 4) lk10_kernel(LKBatch batch, L
                 if (any_border)
                     window_pass<true, true>(B, inx, iny, xa, xb, w00, w01, w10, w11, Ival, Ix, Iy, 0, 0, f0, f1, esum);
                 else
-                    window_pass<false, true>(B, inx, iny, xa, xb, w00, w01, w10, w11, Ival, Ix, Iy, 0, 0, f0, f1, esum);
+                    window_pass_fast<true>(B, inx, iny, xa, simd_flag, w00, w01, w10, w11, Ival, Ix, Iy, f0, f1, esum);
             }
             __syncwarp();
             int tot = 0;

@@ -30,6 +30,8 @@
 // row h-2) the mirrored rolling window yields the same dx and the negated dy bit for bit, so
 // cov_xx / cov_yy are already right and cov_xy only needs its sign flipped back.  Columns
 // outside the image take the reflected cov value of the neighbouring lane/column explicitly.
+#include <algorithm>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -267,8 +269,9 @@ __global__ void __launch_bounds__(NMS_WARPS * 32) nms_candidates_kernel(
     for (int i = threadIdx.x; i < 4096; i += blockDim.x) s_hist[i] = 0;
     __syncthreads();
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int tile = blockIdx.x * NMS_WARPS + wib;
-    const bool tile_ok = tile < tiles_x * tiles_y;            // warp-uniform
+    // persistent blocks: the 16 KB histogram is zeroed and flushed once per block, not once per 4 tiles
+    for (int tile = blockIdx.x * NMS_WARPS + wib; tile < tiles_x * tiles_y; tile += gridDim.x * NMS_WARPS) {
+    const bool tile_ok = true;
     const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
     const int xb = tx * 128 + 4 * lane;
     const int y0 = ty * NMS_ROWS, y_end = tile_ok ? min(y0 + NMS_ROWS, h) : y0;
@@ -379,6 +382,7 @@ __global__ void __launch_bounds__(NMS_WARPS * 32) nms_candidates_kernel(
         for (int j = 0; j < 6; j++) { a[j] = b[j]; b[j] = c[j]; }
     }
     flush();
+    }
     __syncthreads();
     for (int i = threadIdx.x; i < 4096; i += blockDim.x) {
         const int v = s_hist[i];
@@ -392,7 +396,14 @@ void launch_nms_candidates(const float* eig, int eig_pitch, int w, int h, Detect
     cudaMemsetAsync(cand_count, 0, sizeof(int), s);
     cudaMemsetAsync(value_hist, 0, sizeof(int) * 4096, s);
     const int tiles_x = (w + 127) / 128, tiles_y = (h + NMS_ROWS - 1) / NMS_ROWS;
-    const int blocks = (tiles_x * tiles_y + NMS_WARPS - 1) / NMS_WARPS;
+    int blocks = (tiles_x * tiles_y + NMS_WARPS - 1) / NMS_WARPS;
+    static int sm_count = 0;
+    if (!sm_count) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+    }
+    blocks = std::min(blocks, sm_count * 6);                  // 36 KB of shared memory per block: 6 resident per SM
     nms_candidates_kernel<<<blocks, NMS_WARPS * 32, 0, s>>>(eig, eig_pitch, w, h, g, cell_max, quality_level, state,
                                                             state_pitch, cand, cand_cap, cand_count, value_hist,
                                                             tiles_x, tiles_y);

@@ -297,7 +297,7 @@ __global__ void __launch_bounds__(RANK_THREADS) select_rank_emit_kernel(
     if (k == 0) return;
     int m;
     const unsigned thr = (unsigned)suffix_threshold_bin<RANK_THREADS, 64>(kept_hist, k, s_warp, s_res, &m);
-    const bool in_smem = m <= RANK_SMEM_KEYS;
+    const bool in_smem = m < RANK_SMEM_KEYS;
     if (t == 0) s_fill = 0;
     __syncthreads();
     if (in_smem) {
@@ -318,6 +318,7 @@ __global__ void __launch_bounds__(RANK_THREADS) select_rank_emit_kernel(
                 if (keep) s_keys[b + __popc(bal & ((1u << lane) - 1))] = key;
             }
         }
+        if (t == 0) s_keys[m] = 0ull;                        // pad to an even count for the 16-byte loads
         __syncthreads();
     }
     // this CTA's share of the accepted list; one warp per candidate key
@@ -328,7 +329,11 @@ __global__ void __launch_bounds__(RANK_THREADS) select_rank_emit_kernel(
         if ((unsigned)(key >> 48) < thr) continue;          // warp-uniform
         int cnt = 0;
         if (in_smem) {
-            for (int j = lane; j < m; j += 32) cnt += s_keys[j] > key ? 1 : 0;
+            const ulonglong2* s2 = reinterpret_cast<const ulonglong2*>(s_keys);
+            for (int j = lane; 2 * j < m; j += 32) {
+                const ulonglong2 q = s2[j];
+                cnt += (q.x > key ? 1 : 0) + (q.y > key ? 1 : 0);
+            }
         } else {                                             // pathological value plateau: scan the global list
             for (int j = lane; j < n; j += 32) cnt += accepted[j] > key ? 1 : 0;
         }
@@ -418,7 +423,7 @@ void launch_select(const unsigned long long* cand, const int* cand_count, int ca
     }
     // keys: [63:32] ordered value, [31:0] address (< w*h); zero keys sort last
     if (limited) {
-        select_rank_emit_kernel<<<sm_count < 64 ? sm_count : 64, RANK_THREADS, RANK_SMEM_KEYS * sizeof(unsigned long long), s>>>(
+        select_rank_emit_kernel<<<sm_count, RANK_THREADS, RANK_SMEM_KEYS * sizeof(unsigned long long), s>>>(
             ws.accepted, ws.accepted_count, ws.kept_hist, max_corners, w, kps_out, kps_cap, kps_count);
     } else {
         size_t temp = ws.cub_temp_bytes;

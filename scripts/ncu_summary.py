@@ -25,6 +25,22 @@ for row in r[2:]:
         if w in hdr:
             i = hdr.index(w)
             print(f"  {w} = {row[i]} {units[i]}")
+    stalls = []
+    for i, h in enumerate(hdr):
+        if h.startswith("smsp__average_warps_issue_stalled_") and h.endswith("_per_issue_active.ratio"):
+            try:
+                stalls.append((float(row[i]), h[len("smsp__average_warps_issue_stalled_"):-len("_per_issue_active.ratio")]))
+            except ValueError:
+                pass
+    print("  stalls per issue: " + ", ".join(f"{n} {v:.2f}" for v, n in sorted(stalls, reverse=True)[:8]))
+    pipes = []
+    for i, h in enumerate(hdr):
+        if h.startswith("sm__inst_executed_pipe_") and h.endswith(".avg.pct_of_peak_sustained_active"):
+            try:
+                pipes.append((float(row[i]), h[len("sm__inst_executed_pipe_"):-len(".avg.pct_of_peak_sustained_active")]))
+            except ValueError:
+                pass
+    print("  pipes % of peak: " + ", ".join(f"{n} {v:.1f}" for v, n in sorted(pipes, reverse=True)[:6]))
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"], capture_output=True, text=True).stdout
 rows = list(csv.reader(src.splitlines()))
 cur = None
