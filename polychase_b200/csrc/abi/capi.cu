@@ -147,8 +147,9 @@ static int build_pyramid(pc_ctx* c, FrameSlot* f, const uint8_t* img_dev, size_t
     if (channels == 3) launch_rgb_to_gray(img_dev, stride, f->level[0], s);
     else launch_copy_gray(img_dev, stride, f->level[0], s);
     for (int L = 1; L < f->levels; L++) launch_pyr_down(f->level[L - 1], f->level[L], s);
+    launch_pad_border(f->level, f->levels, s);
     span_end(c, s);
-    return check_launch(c, "gray+pyramid", f->levels + (channels == 3 && (w % 16) ? 1 : 0));
+    return check_launch(c, "gray+pyramid", f->levels + 1 + (channels == 3 && (w % 16) ? 1 : 0));
 }
 
 static int run_detector(pc_ctx* c, FrameSlot* f, const pc_gftt_opts* go, cudaStream_t s) {
@@ -171,7 +172,7 @@ static int run_detector(pc_ctx* c, FrameSlot* f, const pc_gftt_opts* go, cudaStr
     span_end(c, s);
     f->has_kps = true;
     f->n_kps_host = -1;
-    return check_launch(c, "detector", go->max_corners > 0 ? 7 : 6);
+    return check_launch(c, "detector", go->max_corners > 0 ? 8 : 6);
 }
 
 static LKParams make_lk_params(const pc_flow_opts* fo) {
@@ -235,7 +236,7 @@ pc_ctx::~pc_ctx() {
     if (d2h) cudaStreamSynchronize(d2h);
     if (track && track->stream) cudaStreamSynchronize(track->stream);
     for (auto& s : slots) {
-        if (s.level[0].data) cudaFree(s.level[0].data);
+        cudaFree(s.base);
         cudaFree(s.kps); cudaFree(s.n_kps);
     }
     cudaFree(eig); cudaFree(state); cudaFree(cell_max); cudaFree(cand); cudaFree(cand_count);
@@ -337,17 +338,21 @@ int pc_create(const pc_limits* limits, pc_ctx** out) {
         int lw = W, lh = H;
         size_t offs[kMaxLevels];
         int pitches[kMaxLevels];
-        for (int L = 0; L < kMaxLevels; L++) {
-            pitches[L] = (lw + 127) / 128 * 128;
+        for (int L = 0; L < kMaxLevels; L++) {                  // image + REFLECT_101 apron (kernels.h)
+            pitches[L] = (lw + 2 * kPadX + 127) / 128 * 128;
             offs[L] = total;
-            total += (size_t)pitches[L] * lh;
+            total += (size_t)pitches[L] * (lh + 2 * kPadY);
             total = (total + 255) / 256 * 256;
             lw = (lw + 1) / 2; lh = (lh + 1) / 2;
         }
         uint8_t* base = nullptr;
-        total += 256;   // lk10.cu stages patches with 4-byte loads that may run a few bytes past a row
+        total += 256;   // lk10.cu reads aligned words that may run a few bytes past the apron
         PC_CUDA(nullptr, cudaMalloc(&base, total));
-        for (int L = 0; L < kMaxLevels; L++) { s.level[L].data = base + offs[L]; s.level[L].pitch = pitches[L]; }
+        s.base = base;
+        for (int L = 0; L < kMaxLevels; L++) {
+            s.level[L].data = base + offs[L] + (size_t)kPadY * pitches[L] + kPadX;
+            s.level[L].pitch = pitches[L];
+        }
         PC_CUDA(nullptr, cudaMalloc(&s.kps, sizeof(float) * 2 * cap));
         PC_CUDA(nullptr, cudaMalloc(&s.n_kps, sizeof(int) * 4));
         PC_CUDA(nullptr, cudaMemset(s.n_kps, 0, sizeof(int) * 4));

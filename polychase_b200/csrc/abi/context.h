@@ -20,7 +20,8 @@ struct FrameSlot {
     int32_t frame_id = 0;
     uint64_t stamp = 0;
     int w = 0, h = 0, levels = 0;
-    Image8 level[kMaxLevels];     // allocated once at the context's max size
+    uint8_t* base = nullptr;      // the slot's one allocation
+    Image8 level[kMaxLevels];     // allocated once at the context's max size (data = pixel (0,0) inside the apron)
     float* kps = nullptr;         // device, max_features x 2
     int* n_kps = nullptr;         // device count
     int* n_accepted = nullptr;    // device: kept corners before the max_corners cut

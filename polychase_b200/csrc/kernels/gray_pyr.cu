@@ -8,6 +8,8 @@
 // shared-memory tiles with word-wide fills on the pyramid levels.  The Scharr derivative
 // images OpenCV materialises per level (4 B/px) are never written: the LK kernel derives
 // them from the level inside its window (lk.cu).
+#include <algorithm>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -132,6 +134,46 @@ __global__ void __launch_bounds__(256) pyr_down_kernel(const uint8_t* __restrict
 void launch_pyr_down(Image8 src, Image8 dst, cudaStream_t s) {
     dim3 grid((dst.w + PD_TW - 1) / PD_TW, (dst.h + PD_TH - 1) / PD_TH);
     pyr_down_kernel<<<grid, 256, 0, s>>>(src.data, src.w, src.h, src.pitch, dst.data, dst.w, dst.h, dst.pitch);
+}
+
+// ---- apron ---------------------------------------------------------------------------
+struct PadPlanes {
+    uint8_t* data[kMaxLevels];
+    int w[kMaxLevels], h[kMaxLevels], pitch[kMaxLevels];
+};
+
+__global__ void __launch_bounds__(256) pad_border_kernel(PadPlanes P) {
+    const int L = blockIdx.y;
+    const int w = P.w[L], h = P.h[L], pitch = P.pitch[L];
+    uint8_t* img = P.data[L];
+    const int full_w = w + 2 * kPadX;
+    const int n_rows = 2 * kPadY * full_w;                 // top + bottom bands (with corners)
+    const int n_cols = 2 * kPadX * h;                      // left + right bands
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_rows + n_cols; i += gridDim.x * blockDim.x) {
+        int x, y;
+        if (i < n_rows) {
+            const int r = i / full_w;
+            x = i - r * full_w - kPadX;
+            y = r < kPadY ? r - kPadY : h + (r - kPadY);
+        } else {
+            const int j = i - n_rows;
+            y = j / (2 * kPadX);
+            const int c = j - y * (2 * kPadX);
+            x = c < kPadX ? c - kPadX : w + (c - kPadX);
+        }
+        img[(ptrdiff_t)y * pitch + x] = img[(ptrdiff_t)reflect101(y, h) * pitch + reflect101(x, w)];
+    }
+}
+
+void launch_pad_border(const Image8* planes, int levels, cudaStream_t s) {
+    PadPlanes P{};
+    int most = 0;
+    for (int L = 0; L < levels; L++) {
+        P.data[L] = planes[L].data; P.w[L] = planes[L].w; P.h[L] = planes[L].h; P.pitch[L] = planes[L].pitch;
+        most = std::max(most, 2 * kPadY * (planes[L].w + 2 * kPadX) + 2 * kPadX * planes[L].h);
+    }
+    dim3 grid(std::min((most + 255) / 256, 296), levels);
+    pad_border_kernel<<<grid, 256, 0, s>>>(P);
 }
 
 }  // namespace pc

@@ -9,8 +9,13 @@ namespace pc {
 
 constexpr int kMaxLevels = 6;
 
+// Pyramid levels of the frame ring carry a REFLECT_101 apron of kPadX columns / kPadY rows around
+// the image (what cv::buildOpticalFlowPyramid's winSize padding gives OpenCV's LK): the 10x10 LK
+// kernel reads windows that hang over the image edge without any border arithmetic.
+constexpr int kPadX = 16, kPadY = 12;
+
 struct Image8 {          // one pitched u8 plane in HBM
-    uint8_t* data = nullptr;
+    uint8_t* data = nullptr;   // pixel (0,0)
     int w = 0, h = 0;
     int pitch = 0;       // bytes per row, multiple of 128
 };
@@ -25,6 +30,8 @@ struct PyramidView {     // what the LK kernel sees of one frame
 void launch_rgb_to_gray(const uint8_t* rgb, size_t stride, Image8 gray, cudaStream_t s);
 void launch_copy_gray(const uint8_t* src, size_t stride, Image8 gray, cudaStream_t s);
 void launch_pyr_down(Image8 src, Image8 dst, cudaStream_t s);
+// Fills the apron (kPadX / kPadY, BORDER_REFLECT_101) of `levels` planes in one launch.
+void launch_pad_border(const Image8* planes, int levels, cudaStream_t s);
 
 // ---- K4/K5: min-eigenvalue map, per-cell max, threshold + NMS (mineig.cu) -------------
 struct DetectGrid {

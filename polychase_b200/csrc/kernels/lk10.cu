@@ -19,9 +19,10 @@
 //     then bottom row, rounding constant folded into the first accumulator.
 //   * template: Scharr derivatives are formed separably on bytes packed two per register
 //     (16-bit fields: |3a+10b+3c| <= 4080, differences biased by +256), once per tap row.
-//   * borders: REFLECT_101 on the image, zero derivative taps outside it (the padding OpenCV's
-//     buildOpticalFlowPyramid applies); a warp takes the reflecting variant of a pass only when
-//     one of its keypoints' windows touches the border at that level.
+//   * borders: the pyramid levels carry a REFLECT_101 apron, so windows that hang over the image
+//     edge need no index arithmetic; derivative taps outside the image are zeroed (the padding
+//     OpenCV's buildOpticalFlowPyramid applies) in a masked variant of the template pass that a
+//     warp takes only when one of its keypoints' patches leaves the image at that level.
 // Integer stages are exact and float stages use explicit-rounding intrinsics (file is compiled
 // with -fmad=false), so results are bit-identical to the oracle (tests/test_gpu_analyze.py).
 #include "common.cuh"
@@ -65,119 +66,35 @@ __device__ __forceinline__ uint32_t pack_weights(int lo, int hi) {
 }
 
 // tail + ((q0 + q2) + (q1 + q3)) over the five chain totals of a pentad (every lane of the
-// pentad gets the same bits)
-__device__ __forceinline__ float pentad_total(float v, int base) {
-    const float q0 = __shfl_sync(FULL, v, base), q1 = __shfl_sync(FULL, v, base + 1);
-    const float q2 = __shfl_sync(FULL, v, base + 2), q3 = __shfl_sync(FULL, v, base + 3);
+// pentad gets the same bits: float addition is commutative, so the pairwise exchange gives each
+// SIMD lane the same two partial sums)
+__device__ __forceinline__ float pentad_total(float v, int base, int role) {
+    const float a = __fadd_rn(v, __shfl_sync(FULL, v, base + ((role ^ 2) & 3)));       // q0+q2 | q1+q3 (roles 0..3)
+    const float b = __fadd_rn(a, __shfl_sync(FULL, a, base + ((role ^ 1) & 3)));       // (q0+q2)+(q1+q3)
+    const float quad = __shfl_sync(FULL, b, base);
     const float tail = __shfl_sync(FULL, v, base + 4);
-    return __fadd_rn(tail, __fadd_rn(__fadd_rn(q0, q2), __fadd_rn(q1, q3)));
+    return __fadd_rn(tail, quad);
 }
 
-// ---- template: Ival / Ix / Iy of the lane's 20 pixels + its chain of A11, A12, A22 terms ------
-// Pixel arrays are indexed [2 * row + s], s = 0 for the lane's first column (xa), 1 for xb.
-template <bool BORDER>
-__device__ __forceinline__ void template_pass(const LevelRef& A, int ipx, int ipy, int xa, int xb, int w00, int w01,
-                                              int w10, int w11, int (&Ival)[20], int (&Ix)[20], int (&Iy)[20],
-                                              float& a11, float& a12, float& a22) {
-    // byte offsets of the 4 source columns (X-1 .. X+2) of each column set, and tap validity
-    int col[2][4];
-    bool tap_in[2][2];
-#pragma unroll
-    for (int s = 0; s < 2; s++) {
-        const int X = ipx + (s ? xb : xa);
-#pragma unroll
-        for (int i = 0; i < 4; i++) col[s][i] = BORDER ? reflect101(X - 1 + i, A.w) : X - 1 + i;
-        tap_in[s][0] = (unsigned)X < (unsigned)A.w;
-        tap_in[s][1] = (unsigned)(X + 1) < (unsigned)A.w;
-    }
-    const uint32_t wa = pack_weights(w00, w01), wb = pack_weights(w10, w11);
-    uint32_t E[2][3] = {}, O[2][3] = {};  // rolling rows: bytes (0,2) and (1,3) in 16-bit fields
-    int ival_top[2] = {0, 0};           // w00/w01 half of the pixel row being formed (+ rounding)
-    int tx[2] = {0, 0}, ty[2] = {0, 0};  // w00/w01 half of the derivative interpolation (+ rounding)
-    a11 = 0.f; a12 = 0.f; a22 = 0.f;
-#pragma unroll
-    for (int rr = 0; rr < WIN + 3; rr++) {          // source rows ipy-1 .. ipy+11
-        const int Y = BORDER ? reflect101(ipy - 1 + rr, A.h) : ipy - 1 + rr;
-        const uint8_t* row = A.img + (size_t)Y * A.pitch;
-        uint32_t P[2];
-#pragma unroll
-        for (int s = 0; s < 2; s++) {
-            const uint32_t g0 = row[col[s][0]], g1 = row[col[s][1]], g2 = row[col[s][2]], g3 = row[col[s][3]];
-            E[s][0] = E[s][1]; E[s][1] = E[s][2]; E[s][2] = g0 | (g2 << 16);
-            O[s][0] = O[s][1]; O[s][1] = O[s][2]; O[s][2] = g1 | (g3 << 16);
-            P[s] = g1 | (g2 << 8);
-        }
-        // image value: pixel row y uses source rows rr = y+1 (top) and y+2 (bottom)
-        if (rr >= 2) {
-            const int y = rr - 2;
-            if (y < WIN) {
-#pragma unroll
-                for (int s = 0; s < 2; s++) Ival[2 * y + s] = dp2a_su(wb, P[s], ival_top[s]) >> (W_BITS - 5);
-            }
-        }
-        if (rr >= 1 && rr <= WIN) {
-#pragma unroll
-            for (int s = 0; s < 2; s++) ival_top[s] = dp2a_su(wa, P[s], 1 << (W_BITS - 5 - 1));
-        }
-        // derivative tap row t (image row ipy + t) uses source rows rr-2, rr-1, rr
-        if (rr >= 2) {
-            const int t = rr - 2;
-            const bool row_in = !BORDER || (unsigned)(ipy + t) < (unsigned)A.h;
-#pragma unroll
-            for (int s = 0; s < 2; s++) {
-                const uint32_t VE = 3u * (E[s][0] + E[s][2]) + 10u * E[s][1];
-                const uint32_t VO = 3u * (O[s][0] + O[s][2]) + 10u * O[s][1];
-                const uint32_t UE = E[s][2] + 0x01000100u - E[s][0];
-                const uint32_t UO = O[s][2] + 0x01000100u - O[s][0];
-                int dx0 = (int)(VE >> 16) - (int)(VE & 0xffffu);
-                int dx1 = (int)(VO >> 16) - (int)(VO & 0xffffu);
-                const int u0 = UE & 0xffffu, u2 = UE >> 16, u1 = UO & 0xffffu, u3 = UO >> 16;
-                int dy0 = 3 * (u0 + u2) + 10 * u1 - 4096;
-                int dy1 = 3 * (u1 + u3) + 10 * u2 - 4096;
-                if (BORDER) {
-                    if (!(row_in && tap_in[s][0])) { dx0 = 0; dy0 = 0; }
-                    if (!(row_in && tap_in[s][1])) { dx1 = 0; dy1 = 0; }
-                }
-                if (t >= 1) {                       // bottom half completes pixel row t-1
-                    const int y = t - 1;
-                    const int ix = (tx[s] + dx0 * w10 + dx1 * w11) >> W_BITS;
-                    const int iy = (ty[s] + dy0 * w10 + dy1 * w11) >> W_BITS;
-                    Ix[2 * y + s] = ix;
-                    Iy[2 * y + s] = iy;
-                }
-                if (t < WIN) {
-                    tx[s] = dx0 * w00 + dx1 * w01 + (1 << (W_BITS - 1));
-                    ty[s] = dy0 * w00 + dy1 * w01 + (1 << (W_BITS - 1));
-                }
-            }
-            if (t >= 1) {
-                const int y = t - 1;
-#pragma unroll
-                for (int s = 0; s < 2; s++) {       // chain order: row by row, first column then second
-                    const int ix = Ix[2 * y + s], iy = Iy[2 * y + s];
-                    a11 = __fadd_rn(a11, (float)(ix * ix));
-                    a12 = __fadd_rn(a12, (float)(ix * iy));
-                    a22 = __fadd_rn(a22, (float)(iy * iy));
-                }
-            }
-        }
-    }
-}
-
-// ---- interior variants: aligned 32-bit loads + funnel shifts instead of byte gathers -----------
-// A lane's two column sets are 4 apart (SIMD chains: columns c and c+4) or adjacent (tail chain:
-// columns 8 and 9), so everything it needs from one source row lies in the 12 bytes that start at
-// the 4-byte boundary below its first byte: three aligned word loads off ONE row pointer
-// (immediate offsets 0/4/8) replace eight (template) or four (window) byte loads with their own
-// 64-bit addresses.  `step` is 8 * (first byte & 3); `simd` selects the column-set distance.
-// Frame levels are padded (pitch multiple of 128, slack after the last level), so the words may
-// run past the bytes actually used.
+// ---- row access: aligned 32-bit loads + funnel shifts -------------------------------------------
+// Pyramid levels carry a REFLECT_101 apron (kPadX / kPadY, kernels.h), so a window that hangs over
+// the image edge is read like any other.  A lane's two column sets are 4 apart (SIMD chains:
+// columns c and c+4) or adjacent (tail chain: columns 8 and 9), so everything it needs from one
+// source row lies in the 12 bytes that start at the 4-byte boundary below its first byte: three
+// aligned word loads off ONE row pointer (immediate offsets 0/4/8) and funnel shifts replace
+// per-byte gathers.  `step` is 8 * (first byte & 3); `simd` selects the column-set distance.
 __device__ __forceinline__ void load_row_words(const uint8_t* rowp, uint32_t& w0, uint32_t& w1, uint32_t& w2) {
     const uint32_t* q = reinterpret_cast<const uint32_t*>(rowp);
     w0 = __ldg(q); w1 = __ldg(q + 1); w2 = __ldg(q + 2);
 }
 
-__device__ __forceinline__ void template_pass_fast(const LevelRef& A, int ipx, int ipy, int xa, int simd, int w00,
+// ---- template: Ival / Ix / Iy of the lane's 20 pixels + its chain of A11, A12, A22 terms ------
+// Pixel arrays are indexed [2 * row + s], s = 0 for the lane's first column (xa), 1 for the second.
+// MASK: derivative taps outside the image are zero (cv::buildOpticalFlowPyramid pads the derivative
+// image with BORDER_CONSTANT); a warp takes this variant only when one of its keypoints' 13x13
+// source patches leaves the image.
+template <bool MASK>
+__device__ __forceinline__ void template_pass(const LevelRef& A, int ipx, int ipy, int xa, int simd, int w00,
                                                    int w01, int w10, int w11, int (&Ival)[20], int (&Ix)[20],
                                                    int (&Iy)[20], float& a11, float& a12, float& a22) {
     const int X0 = ipx + xa - 1;                      // first byte of column set 0 (taps X-1 .. X+2)
@@ -185,6 +102,13 @@ __device__ __forceinline__ void template_pass_fast(const LevelRef& A, int ipx, i
     const int step = (X0 & 3) * 8;
     const int step2 = simd ? 0 : 8;                   // tail: set 1 starts one byte after set 0
     const uint32_t wa = pack_weights(w00, w01), wb = pack_weights(w10, w11);
+    bool tap_in[2][2];
+#pragma unroll
+    for (int s = 0; s < 2; s++) {
+        const int X = ipx + xa + (s ? (simd ? 4 : 1) : 0);
+        tap_in[s][0] = (unsigned)X < (unsigned)A.w;
+        tap_in[s][1] = (unsigned)(X + 1) < (unsigned)A.w;
+    }
     uint32_t E[2][3] = {}, O[2][3] = {};
     int ival_top[2] = {0, 0};
     int tx[2] = {0, 0}, ty[2] = {0, 0};
@@ -217,18 +141,23 @@ __device__ __forceinline__ void template_pass_fast(const LevelRef& A, int ipx, i
             for (int s = 0; s < 2; s++) ival_top[s] = dp2a_su(wa, P[s], 1 << (W_BITS - 5 - 1));
         }
         if (rr >= 2) {
-            const int t = rr - 2;
+            const int t = rr - 2;                     // derivative tap row: image row ipy + t
+            const bool row_in = !MASK || (unsigned)(ipy + t) < (unsigned)A.h;
 #pragma unroll
             for (int s = 0; s < 2; s++) {
                 const uint32_t VE = 3u * (E[s][0] + E[s][2]) + 10u * E[s][1];
                 const uint32_t VO = 3u * (O[s][0] + O[s][2]) + 10u * O[s][1];
                 const uint32_t UE = E[s][2] + 0x01000100u - E[s][0];
                 const uint32_t UO = O[s][2] + 0x01000100u - O[s][0];
-                const int dx0 = (int)(VE >> 16) - (int)(VE & 0xffffu);
-                const int dx1 = (int)(VO >> 16) - (int)(VO & 0xffffu);
+                int dx0 = (int)(VE >> 16) - (int)(VE & 0xffffu);
+                int dx1 = (int)(VO >> 16) - (int)(VO & 0xffffu);
                 const int u0 = UE & 0xffffu, u2 = UE >> 16, u1 = UO & 0xffffu, u3 = UO >> 16;
-                const int dy0 = 3 * (u0 + u2) + 10 * u1 - 4096;
-                const int dy1 = 3 * (u1 + u3) + 10 * u2 - 4096;
+                int dy0 = 3 * (u0 + u2) + 10 * u1 - 4096;
+                int dy1 = 3 * (u1 + u3) + 10 * u2 - 4096;
+                if (MASK) {
+                    if (!(row_in && tap_in[s][0])) { dx0 = 0; dy0 = 0; }
+                    if (!(row_in && tap_in[s][1])) { dx1 = 0; dy1 = 0; }
+                }
                 if (t >= 1) {
                     const int y = t - 1;
                     Ix[2 * y + s] = (tx[s] + dx0 * w10 + dx1 * w11) >> W_BITS;
@@ -253,8 +182,9 @@ __device__ __forceinline__ void template_pass_fast(const LevelRef& A, int ipx, i
     }
 }
 
+// ---- one pass over the target window: b1/b2 chain terms (ERR = false) or the L1 error -------
 template <bool ERR>
-__device__ __forceinline__ void window_pass_fast(const LevelRef& B, int inx, int iny, int xa, int simd, int w00,
+__device__ __forceinline__ void window_pass(const LevelRef& B, int inx, int iny, int xa, int simd, int w00,
                                                  int w01, int w10, int w11, const int (&Ival)[20],
                                                  const int (&Ix)[20], const int (&Iy)[20], float& bx, float& by,
                                                  int& esum) {
@@ -296,54 +226,6 @@ __device__ __forceinline__ void window_pass_fast(const LevelRef& B, int inx, int
     }
 }
 
-// ---- one pass over the target window: b1/b2 chain terms (ERR = false) or the L1 error -------
-template <bool BORDER, bool ERR>
-__device__ __forceinline__ void window_pass(const LevelRef& B, int inx, int iny, int xa, int xb, int w00, int w01,
-                                            int w10, int w11, const int (&Ival)[20], const int (&Ix)[20],
-                                            const int (&Iy)[20], int simd_flag, int tail_flag, float& bx, float& by,
-                                            int& esum) {
-    int col[2][2];
-#pragma unroll
-    for (int s = 0; s < 2; s++) {
-        const int X = inx + (s ? xb : xa);
-        col[s][0] = BORDER ? reflect101(X, B.w) : X;
-        col[s][1] = BORDER ? reflect101(X + 1, B.w) : X + 1;
-    }
-    const uint32_t wa = pack_weights(w00, w01), wb = pack_weights(w10, w11);
-    int top[2] = {0, 0};
-    bx = 0.f; by = 0.f; esum = 0;
-#pragma unroll
-    for (int rr = 0; rr <= WIN; rr++) {             // target rows iny .. iny+10
-        const int Y = BORDER ? reflect101(iny + rr, B.h) : iny + rr;
-        const uint8_t* row = B.img + (size_t)Y * B.pitch;
-        uint32_t P[2];
-#pragma unroll
-        for (int s = 0; s < 2; s++) P[s] = (uint32_t)row[col[s][0]] | ((uint32_t)row[col[s][1]] << 8);
-        if (rr >= 1) {
-            const int y = rr - 1;
-            const int d0 = (dp2a_su(wb, P[0], top[0]) >> (W_BITS - 5)) - Ival[2 * y];
-            const int d1 = (dp2a_su(wb, P[1], top[1]) >> (W_BITS - 5)) - Ival[2 * y + 1];
-            if (ERR) {
-                esum += abs(d0) + abs(d1);
-            } else {
-                // SIMD chains add the two columns' integer products before converting (pmaddwd);
-                // the tail chain converts and adds them one by one.  x + (+0) == x keeps one code
-                // path for both kinds of lane.
-                const int mx0 = d0 * Ix[2 * y], mx1 = d1 * Ix[2 * y + 1];
-                const int my0 = d0 * Iy[2 * y], my1 = d1 * Iy[2 * y + 1];
-                bx = __fadd_rn(bx, (float)(mx0 + mx1 * simd_flag));
-                by = __fadd_rn(by, (float)(my0 + my1 * simd_flag));
-                bx = __fadd_rn(bx, (float)(mx1 * tail_flag));
-                by = __fadd_rn(by, (float)(my1 * tail_flag));
-            }
-        }
-        if (rr < WIN) {
-            top[0] = dp2a_su(wa, P[0], 1 << (W_BITS - 5 - 1));
-            top[1] = dp2a_su(wa, P[1], 1 << (W_BITS - 5 - 1));
-        }
-    }
-}
-
 __global__ void __launch_bounds__(LK_WARPS * 32, 4) lk10_kernel(LKBatch batch, LKParams prm) {
     // large skips take several times more iterations (slow pairs are appended last): schedule
     // them first so the launch does not end on a tail of long blocks
@@ -356,14 +238,15 @@ __global__ void __launch_bounds__(LK_WARPS * 32, 4) lk10_kernel(LKBatch batch, L
     const bool valid = grp < PTS_PER_WARP && pi < npts;
     if (!__any_sync(FULL, valid)) return;
 
-    const int simd_flag = role < 4 ? 1 : 0, tail_flag = 1 - simd_flag;
-    const int xa = simd_flag ? role : 8, xb = simd_flag ? role + 4 : 9;
+    const int simd_flag = role < 4 ? 1 : 0;
+    const int xa = simd_flag ? role : 8;              // first column of the lane's chain (second: +4, tail +1)
 
     float ptx = 0.f, pty = 0.f;
     if (valid) { ptx = pr.pts[2 * pi]; pty = pr.pts[2 * pi + 1]; }
     const float halfw = (WIN - 1) * 0.5f;
     const int nlevels = min(min(pr.a.levels, pr.b.levels), prm.max_level + 1);
     const double eps2 = prm.eps * prm.eps;
+    const float eps2_lo = (float)(eps2 * (1.0 - 1e-6)), eps2_hi = (float)(eps2 * (1.0 + 1e-6));
     const float FLT_SCALE = 1.f / (float)(1 << 20);
     float nextx = 0.f, nexty = 0.f;
     int status = 1;
@@ -394,14 +277,14 @@ __global__ void __launch_bounds__(LK_WARPS * 32, 4) lk10_kernel(LKBatch batch, L
             const bool t_inside = ipx >= 1 && ipy >= 1 && ipx + WIN + 1 < A.w && ipy + WIN + 1 < A.h;
             const bool any_border = __any_sync(FULL, act && !t_inside);
             if (act) {
-                if (any_border) template_pass<true>(A, ipx, ipy, xa, xb, w00, w01, w10, w11, Ival, Ix, Iy, a11, a12, a22);
-                else template_pass_fast(A, ipx, ipy, xa, simd_flag, w00, w01, w10, w11, Ival, Ix, Iy, a11, a12, a22);
+                if (any_border) template_pass<true>(A, ipx, ipy, xa, simd_flag, w00, w01, w10, w11, Ival, Ix, Iy, a11, a12, a22);
+                else template_pass<false>(A, ipx, ipy, xa, simd_flag, w00, w01, w10, w11, Ival, Ix, Iy, a11, a12, a22);
             }
             __syncwarp();
         }
-        const float A11 = __fmul_rn(pentad_total(a11, base), FLT_SCALE);
-        const float A12 = __fmul_rn(pentad_total(a12, base), FLT_SCALE);
-        const float A22 = __fmul_rn(pentad_total(a22, base), FLT_SCALE);
+        const float A11 = __fmul_rn(pentad_total(a11, base, role), FLT_SCALE);
+        const float A12 = __fmul_rn(pentad_total(a12, base, role), FLT_SCALE);
+        const float A22 = __fmul_rn(pentad_total(a22, base, role), FLT_SCALE);
         float D = __fsub_rn(__fmul_rn(A11, A22), __fmul_rn(A12, A12));
         const float dA = __fsub_rn(A11, A22);
         const float rad = __fadd_rn(__fmul_rn(dA, dA), __fmul_rn(__fmul_rn(4.f, A12), A12));
@@ -419,32 +302,32 @@ __global__ void __launch_bounds__(LK_WARPS * 32, 4) lk10_kernel(LKBatch batch, L
         for (int j = 0; j < prm.iters; j++) {
             if (!__any_sync(FULL, iterating)) break;
             const int inx = __float2int_rd(nx), iny = __float2int_rd(ny);
-            if (iterating && (inx < -WIN || inx >= B.w || iny < -WIN || iny >= B.h)) {
-                if (level == 0) status = 0;
+            if (iterating && ((unsigned)(inx + WIN) >= (unsigned)(B.w + WIN) || (unsigned)(iny + WIN) >= (unsigned)(B.h + WIN))) {
+                if (level == 0) status = 0;                  // inx < -WIN || inx >= B.w || iny < -WIN || iny >= B.h
                 iterating = false;
             }
             bilinear_weights(__fsub_rn(nx, (float)inx), __fsub_rn(ny, (float)iny), w00, w01, w10, w11);
-            const bool inside = inx >= 0 && iny >= 0 && inx + WIN < B.w && iny + WIN < B.h;
-            const bool any_border = __any_sync(FULL, iterating && !inside);
             float bx = 0.f, by = 0.f;
             int unused = 0;
-            if (iterating) {
-                if (any_border)
-                    window_pass<true, false>(B, inx, iny, xa, xb, w00, w01, w10, w11, Ival, Ix, Iy, simd_flag, tail_flag, bx, by, unused);
-                else
-                    window_pass_fast<false>(B, inx, iny, xa, simd_flag, w00, w01, w10, w11, Ival, Ix, Iy, bx, by, unused);
-            }
+            if (iterating) window_pass<false>(B, inx, iny, xa, simd_flag, w00, w01, w10, w11, Ival, Ix, Iy, bx, by, unused);
             __syncwarp();
-            const float b1 = __fmul_rn(pentad_total(bx, base), FLT_SCALE);
-            const float b2 = __fmul_rn(pentad_total(by, base), FLT_SCALE);
+            const float b1 = __fmul_rn(pentad_total(bx, base, role), FLT_SCALE);
+            const float b2 = __fmul_rn(pentad_total(by, base, role), FLT_SCALE);
             if (iterating) {
                 const float dx = __fmul_rn(__fsub_rn(__fmul_rn(A12, b2), __fmul_rn(A22, b1)), D);
                 const float dy = __fmul_rn(__fsub_rn(__fmul_rn(A12, b1), __fmul_rn(A11, b2)), D);
                 nx = __fadd_rn(nx, dx); ny = __fadd_rn(ny, dy);
                 nextx = __fadd_rn(nx, halfw); nexty = __fadd_rn(ny, halfw);
-                if (__dadd_rn(__dmul_rn((double)dx, (double)dx), __dmul_rn((double)dy, (double)dy)) <= eps2) {
+                // OpenCV tests dx*dx + dy*dy <= eps^2 in double; the float sum decides it except within
+                // 1e-6 (relative) of the threshold, where the double expression is evaluated
+                const float d2 = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+                bool small = d2 <= eps2_lo;
+                if (!small && d2 < eps2_hi)
+                    small = __dadd_rn(__dmul_rn((double)dx, (double)dx), __dmul_rn((double)dy, (double)dy)) <= eps2;
+                // fabs((double)v) < 0.01  <=>  fabsf(v) <= 0.01f: 0.01f is the largest float below 0.01
+                if (small) {
                     iterating = false;
-                } else if (j > 0 && fabs((double)__fadd_rn(dx, pdx)) < 0.01 && fabs((double)__fadd_rn(dy, pdy)) < 0.01) {
+                } else if (j > 0 && fabsf(__fadd_rn(dx, pdx)) <= 0.01f && fabsf(__fadd_rn(dy, pdy)) <= 0.01f) {
                     nextx = __fsub_rn(nextx, __fmul_rn(dx, 0.5f));
                     nexty = __fsub_rn(nexty, __fmul_rn(dy, 0.5f));
                     iterating = false;
@@ -462,16 +345,9 @@ __global__ void __launch_bounds__(LK_WARPS * 32, 4) lk10_kernel(LKBatch batch, L
                 want = false;
             }
             bilinear_weights(__fsub_rn(fx, (float)inx), __fsub_rn(fy, (float)iny), w00, w01, w10, w11);
-            const bool inside = inx >= 0 && iny >= 0 && inx + WIN < B.w && iny + WIN < B.h;
-            const bool any_border = __any_sync(FULL, want && !inside);
             int esum = 0;
             float f0, f1;
-            if (want) {
-                if (any_border)
-                    window_pass<true, true>(B, inx, iny, xa, xb, w00, w01, w10, w11, Ival, Ix, Iy, 0, 0, f0, f1, esum);
-                else
-                    window_pass_fast<true>(B, inx, iny, xa, simd_flag, w00, w01, w10, w11, Ival, Ix, Iy, f0, f1, esum);
-            }
+            if (want) window_pass<true>(B, inx, iny, xa, simd_flag, w00, w01, w10, w11, Ival, Ix, Iy, f0, f1, esum);
             __syncwarp();
             int tot = 0;
 #pragma unroll

@@ -284,19 +284,32 @@ __global__ void __launch_bounds__(256) compact_strong_kernel(const unsigned long
 constexpr int RANK_THREADS = 1024;
 constexpr int RANK_SMEM_KEYS = 16384;                       // 128 KB of dynamic shared memory
 
+// One CTA scans the 65536-bin histogram of kept keys once per frame (sel[2] = threshold bin,
+// sel[3] = number of keys at or above it); the ranking CTAs only read those two ints.
+__global__ void __launch_bounds__(RANK_THREADS) rank_threshold_kernel(const int* __restrict__ accepted_count,
+                                                                      const int* __restrict__ kept_hist,
+                                                                      int max_corners, int kps_cap,
+                                                                      int* __restrict__ sel) {
+    __shared__ int s_warp[RANK_THREADS / 32], s_res[8];
+    const int k = min(min(max_corners, *accepted_count), kps_cap);
+    int m = 0, thr = 0;
+    if (k > 0) thr = suffix_threshold_bin<RANK_THREADS, 64>(kept_hist, k, s_warp, s_res, &m);
+    if (threadIdx.x == 0) { sel[2] = thr; sel[3] = m; }
+}
+
 __global__ void __launch_bounds__(RANK_THREADS) select_rank_emit_kernel(
     const unsigned long long* __restrict__ accepted, const int* __restrict__ accepted_count,
-    const int* __restrict__ kept_hist, int max_corners, int w, float* __restrict__ kps, int kps_cap,
+    const int* __restrict__ sel, int max_corners, int w, float* __restrict__ kps, int kps_cap,
     int* __restrict__ kps_count) {
     extern __shared__ __align__(16) unsigned long long s_keys[];
-    __shared__ int s_warp[RANK_THREADS / 32], s_res[8], s_fill;
+    __shared__ int s_fill;
     const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
     const int n = *accepted_count;
     const int k = min(min(max_corners, n), kps_cap);
     if (blockIdx.x == 0 && t == 0) *kps_count = k;
     if (k == 0) return;
-    int m;
-    const unsigned thr = (unsigned)suffix_threshold_bin<RANK_THREADS, 64>(kept_hist, k, s_warp, s_res, &m);
+    const unsigned thr = (unsigned)sel[2];
+    const int m = sel[3];
     const bool in_smem = m < RANK_SMEM_KEYS;
     if (t == 0) s_fill = 0;
     __syncthreads();
@@ -423,8 +436,9 @@ void launch_select(const unsigned long long* cand, const int* cand_count, int ca
     }
     // keys: [63:32] ordered value, [31:0] address (< w*h); zero keys sort last
     if (limited) {
+        rank_threshold_kernel<<<1, RANK_THREADS, 0, s>>>(ws.accepted_count, ws.kept_hist, max_corners, kps_cap, ws.sel);
         select_rank_emit_kernel<<<sm_count, RANK_THREADS, RANK_SMEM_KEYS * sizeof(unsigned long long), s>>>(
-            ws.accepted, ws.accepted_count, ws.kept_hist, max_corners, w, kps_out, kps_cap, kps_count);
+            ws.accepted, ws.accepted_count, ws.sel, max_corners, w, kps_out, kps_cap, kps_count);
     } else {
         size_t temp = ws.cub_temp_bytes;
         cub::DeviceRadixSort::SortKeysDescending(ws.cub_temp, temp, ws.accepted, ws.sorted, ws.cap, 0, 64, s);
