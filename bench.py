@@ -179,6 +179,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-track", action="store_true", help="time detect+LK only (no per-frame PnP sweep)")
+    ap.add_argument("--diag", action="store_true",
+                    help="also time upload-only and download-only legs and the raw H2D copy rate (stderr)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -376,6 +378,29 @@ def main():
             ctx.lib.pc_memcpy_d2h(ctx.h, ctypes.c_void_p(host_ptr + i * frame_bytes),
                                   ctypes.c_void_p(dev_frames + i * frame_bytes), frame_bytes)
         e2e_res = timed_leg(capi.PC_MEM_HOST_PINNED, host_ptr, ring, download=True)
+        if args.diag and rank == 0:
+            import sys
+            up = timed_leg(capi.PC_MEM_HOST_PINNED, host_ptr, ring, download=False)
+            down = timed_leg(capi.PC_MEM_DEVICE, dev_frames, n_frames, download=True)
+            src = torch.empty(frame_bytes, dtype=torch.uint8).pin_memory()
+            dst = torch.empty(frame_bytes, dtype=torch.uint8, device="cuda")
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+            dst.copy_(src, non_blocking=True)
+            torch.cuda.synchronize()
+            ev[0].record()
+            for _ in range(20):
+                dst.copy_(src, non_blocking=True)
+            ev[1].record()
+            torch.cuda.synchronize()
+            h2d_gbs = 20 * frame_bytes / (ev[0].elapsed_time(ev[1]) * 1e-3) / 1e9
+            print(json.dumps({"diag": {"resident_ms_per_step": res["dev_ms"] / args.steps,
+                                       "resident_wall_ms_per_step": 1e3 * res["wall_s"] / args.steps,
+                                       "e2e_ms_per_step": e2e_res["dev_ms"] / args.steps,
+                                       "upload_only_ms_per_step": up["dev_ms"] / args.steps,
+                                       "download_only_ms_per_step": down["dev_ms"] / args.steps,
+                                       "h2d_pinned_gbs": h2d_gbs,
+                                       "h2d_ms_per_step_at_that_rate": fps * frame_bytes / h2d_gbs / 1e6}}),
+                  file=sys.stderr)
         ctx.pinned_free(host_ptr)
         e2e = e2e_res
 

@@ -225,6 +225,38 @@ static void free_pair_out(PairOut& o, bool pinned) {
     o = PairOut{};
 }
 
+// Row slab of one analyzer stage: [8 counts, padded to 128 B | pair k: idx (cap u32), tgt (2 cap f32),
+// err (cap f32)] with cap rounded to 32 rows so every array starts on a 128-byte line.
+static int alloc_stage_rows(pc_ctx* c, Stage& st, int cap) {
+    const size_t capr = ((size_t)cap + 31) / 32 * 32;
+    const size_t pair_bytes = capr * 16;
+    st.rows_bytes = 128 + 8 * pair_bytes;
+    PC_CUDA(c, cudaMalloc(&st.rows_dev, st.rows_bytes));
+    PC_CUDA(c, cudaMallocHost(&st.rows_host, st.rows_bytes));
+    PC_CUDA(c, cudaMemset(st.rows_dev, 0, 128));
+    memset(st.rows_host, 0, 128);
+    for (int side = 0; side < 2; side++) {
+        uint8_t* base = side ? st.rows_host : st.rows_dev;
+        PairOut* o = side ? st.host : st.dev;
+        for (int k = 0; k < 8; k++) {
+            uint8_t* p = base + 128 + k * pair_bytes;
+            o[k].count = reinterpret_cast<int*>(base) + k;
+            o[k].idx = reinterpret_cast<uint32_t*>(p);
+            o[k].tgt = reinterpret_cast<float*>(p + capr * 4);
+            o[k].err = reinterpret_cast<float*>(p + capr * 12);
+        }
+    }
+    return PC_OK;
+}
+
+static void free_stage_rows(Stage& st) {
+    cudaFree(st.rows_dev);
+    cudaFreeHost(st.rows_host);
+    st.rows_dev = st.rows_host = nullptr;
+    st.rows_bytes = 0;
+    for (int k = 0; k < 8; k++) st.dev[k] = st.host[k] = PairOut{};
+}
+
 }  // namespace pc
 
 using namespace pc;
@@ -234,6 +266,8 @@ pc_ctx::~pc_ctx() {
     if (compute) cudaStreamSynchronize(compute);
     if (h2d) cudaStreamSynchronize(h2d);
     if (d2h) cudaStreamSynchronize(d2h);
+    if (d2h_rows) cudaStreamSynchronize(d2h_rows);
+    if (side) cudaStreamSynchronize(side);
     if (track && track->stream) cudaStreamSynchronize(track->stream);
     for (auto& s : slots) {
         cudaFree(s.base);
@@ -247,12 +281,13 @@ pc_ctx::~pc_ctx() {
     cudaFree(rgb_scratch);
     for (auto& st : stages) {
         cudaFree(st.rgb_dev);
-        for (int k = 0; k < 8; k++) { free_pair_out(st.dev[k], false); free_pair_out(st.host[k], true); }
+        free_stage_rows(st);
         cudaFreeHost(st.kps_host); cudaFreeHost(st.counts_host);
         cudaFree(st.trk_result_dev); cudaFreeHost(st.trk_result_host); cudaFreeHost(st.trk_cam_host);
         if (st.tracked) cudaEventDestroy(st.tracked);
         if (st.uploaded) cudaEventDestroy(st.uploaded);
         if (st.gray_done) cudaEventDestroy(st.gray_done);
+        if (st.detected) cudaEventDestroy(st.detected);
         if (st.computed) cudaEventDestroy(st.computed);
         if (st.downloaded) cudaEventDestroy(st.downloaded);
     }
@@ -262,12 +297,15 @@ pc_ctx::~pc_ctx() {
     for (auto e : marks) if (e) cudaEventDestroy(e);
     if (join_a) cudaEventDestroy(join_a);
     if (join_b) cudaEventDestroy(join_b);
+    if (join_c) cudaEventDestroy(join_c);
     if (track) free_track_chain(track);
     if (mesh) free_mesh(mesh);
     if (ba) free_ba(ba);
+    if (side) cudaStreamDestroy(side);
     if (compute) cudaStreamDestroy(compute);
     if (h2d) cudaStreamDestroy(h2d);
     if (d2h) cudaStreamDestroy(d2h);
+    if (d2h_rows) cudaStreamDestroy(d2h_rows);
 }
 
 extern "C" {
@@ -326,9 +364,20 @@ int pc_create(const pc_limits* limits, pc_ctx** out) {
     c->sm_count = prop.multiProcessorCount;
     pc_ctx* cp = c.get();
     PC_CUDA(nullptr, cudaSetDevice(lim.device));
-    PC_CUDA(nullptr, cudaStreamCreateWithFlags(&cp->compute, cudaStreamNonBlocking));
+    {
+        // priorities: track chain (highest, track.cu) > detector / everything else > streaming LK batches.
+        // The analyzer's LK batches run on their own stream, so frame j's batch (ALU / gather bound)
+        // shares the SMs with frame j+1's pyramid + detector (HBM streaming, then short latency-bound
+        // selection launches) instead of running back to back with them.
+        int lo = 0, hi = 0;                        // numerically lower = higher priority
+        PC_CUDA(nullptr, cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        PC_CUDA(nullptr, cudaStreamCreateWithPriority(&cp->compute, cudaStreamNonBlocking, hi < lo ? hi + 1 : lo));
+        const char* e = getenv("PC_LK_STREAM");     // PC_LK_STREAM=0: everything on the compute stream
+        if (!e || atoi(e) != 0) PC_CUDA(nullptr, cudaStreamCreateWithPriority(&cp->side, cudaStreamNonBlocking, lo));
+    }
     PC_CUDA(nullptr, cudaStreamCreateWithFlags(&cp->h2d, cudaStreamNonBlocking));
     PC_CUDA(nullptr, cudaStreamCreateWithFlags(&cp->d2h, cudaStreamNonBlocking));
+    PC_CUDA(nullptr, cudaStreamCreateWithFlags(&cp->d2h_rows, cudaStreamNonBlocking));
 
     const int W = lim.max_width, H = lim.max_height, cap = lim.max_features;
     // frame ring: all levels of a slot in one allocation
@@ -398,6 +447,8 @@ int pc_synchronize(pc_ctx* c) {
     PC_CUDA(c, cudaStreamSynchronize(c->h2d));
     PC_CUDA(c, cudaStreamSynchronize(c->compute));
     PC_CUDA(c, cudaStreamSynchronize(c->d2h));
+    PC_CUDA(c, cudaStreamSynchronize(c->d2h_rows));
+    if (c->side) PC_CUDA(c, cudaStreamSynchronize(c->side));
     if (c->track && c->track->stream) PC_CUDA(c, cudaStreamSynchronize(c->track->stream));
     return PC_OK;
 }
@@ -639,21 +690,20 @@ int pc_analyze_begin(pc_ctx* c, const pc_video_info* vi, const pc_gftt_opts* go,
     if (c->stages.empty()) {
         c->stages.resize(c->lim.pipeline_depth);
         for (auto& st : c->stages) {
-            for (int k = 0; k < 8; k++) {
-                rc = alloc_pair_out(c, st.dev[k], cap, false);
-                if (rc) return rc;
-                rc = alloc_pair_out(c, st.host[k], cap, true);
-                if (rc) return rc;
-            }
+            rc = alloc_stage_rows(c, st, cap);
+            if (rc) return rc;
             PC_CUDA(c, cudaMallocHost(&st.kps_host, sizeof(float) * 2 * cap));
             PC_CUDA(c, cudaMallocHost(&st.counts_host, sizeof(int) * 4));
             PC_CUDA(c, cudaEventCreateWithFlags(&st.uploaded, cudaEventDisableTiming));
             PC_CUDA(c, cudaEventCreateWithFlags(&st.gray_done, cudaEventDisableTiming));
+            PC_CUDA(c, cudaEventCreateWithFlags(&st.detected, cudaEventDisableTiming));
             PC_CUDA(c, cudaEventCreateWithFlags(&st.computed, cudaEventDisableTiming));
             PC_CUDA(c, cudaEventCreateWithFlags(&st.downloaded, cudaEventDisableTiming));
         }
     }
+    if (c->side) PC_CUDA(c, cudaStreamSynchronize(c->side));
     for (auto& s : c->slots) s.used = false;
+    c->download_hint = false;
     c->inflight.clear();
     c->next_stage = 0;
     c->any_pushed = false;
@@ -689,12 +739,17 @@ int pc_mark(pc_ctx* c, int slot) {
     if (!c->join_a) {
         PC_CUDA(c, cudaEventCreateWithFlags(&c->join_a, cudaEventDisableTiming));
         PC_CUDA(c, cudaEventCreateWithFlags(&c->join_b, cudaEventDisableTiming));
+        PC_CUDA(c, cudaEventCreateWithFlags(&c->join_c, cudaEventDisableTiming));
     }
     if (!c->marks[slot]) PC_CUDA(c, cudaEventCreate(&c->marks[slot]));
     PC_CUDA(c, cudaEventRecord(c->join_a, c->h2d));
     PC_CUDA(c, cudaEventRecord(c->join_b, c->d2h));
     PC_CUDA(c, cudaStreamWaitEvent(c->compute, c->join_a, 0));
     PC_CUDA(c, cudaStreamWaitEvent(c->compute, c->join_b, 0));
+    if (c->side) {
+        PC_CUDA(c, cudaEventRecord(c->join_c, c->side));
+        PC_CUDA(c, cudaStreamWaitEvent(c->compute, c->join_c, 0));
+    }
     if (c->track && c->track->stream) {
         PC_CUDA(c, cudaEventRecord(c->track->join, c->track->stream));
         PC_CUDA(c, cudaStreamWaitEvent(c->compute, c->track->join, 0));
@@ -708,6 +763,77 @@ int pc_elapsed_ms(pc_ctx* c, int a, int b, float* ms_out) {
     PC_CUDA(c, cudaEventSynchronize(c->marks[a]));
     PC_CUDA(c, cudaEventSynchronize(c->marks[b]));
     PC_CUDA(c, cudaEventElapsedTime(ms_out, c->marks[a], c->marks[b]));
+    return PC_OK;
+}
+
+// Largest row slab that travels whole (one copy) instead of as size-exact per-array copies.
+static const size_t kSlabCopyMax = 8u << 20;
+
+// Queues the LK batch of a pushed frame -- every pair whose later frame is this one: (j-d -> j) and
+// (j -> j-d), d in {1,2,4,8} -- its compaction, the fused track step and the result downloads.
+static int enqueue_lk(pc_ctx* c, Stage& st, FrameSlot* f) {
+    const int32_t frame_id = st.frame_id;
+    const int32_t first = c->vinfo.first_frame;
+    cudaStream_t lks = c->compute;
+    if (c->side) {
+        // this frame's pyramid and keypoints (and, stream order, those of every earlier frame)
+        PC_CUDA(c, cudaEventRecord(st.detected, c->compute));
+        PC_CUDA(c, cudaStreamWaitEvent(c->side, st.detected, 0));
+        lks = c->side;
+    }
+    LKBatch batch{};
+    batch.cap = c->lim.max_features;
+    if (c->gopts.max_corners > 0) batch.cap = std::min(batch.cap, c->gopts.max_corners);
+    static const int kSkips[4] = {1, 2, 4, 8};   // |image_skips|, opticalflow.cc:76-77
+    int np = 0;
+    for (int k = 0; k < 4 && !st.is_halo; k++) {
+        const int32_t other = frame_id - kSkips[k];
+        if (other < first) continue;
+        FrameSlot* o = find_slot(c, other);
+        if (!o) return fail(c, PC_ERR_STATE, "frame " + std::to_string(other) + " fell out of the ring");
+        st.from[np] = other; st.to[np] = frame_id;
+        fill_pair(c, batch.pair[np], *o, *f, np, st.dev[np]);
+        np++;
+        st.from[np] = frame_id; st.to[np] = other;
+        fill_pair(c, batch.pair[np], *f, *o, np, st.dev[np]);
+        np++;
+    }
+    // presets may exceed max_corners
+    for (int k = 0; k < np; k++) {
+        const FrameSlot* src = find_slot(c, st.from[k]);
+        if (src->n_kps_host > batch.cap) batch.cap = src->n_kps_host;
+    }
+    batch.num_pairs = np;
+    st.num_pairs = np;
+    int rc;
+    if (np > 0) {
+        const LKParams p = make_lk_params(&c->fopts);
+        span_begin(c, KF_LK, lks);
+        launch_lk(batch, p, lks);
+        span_end(c, lks);
+        span_begin(c, KF_COMPACT, lks);
+        launch_lk_compact(batch, lks);
+        span_end(c, lks);
+        rc = check_launch(c, "lk batch", 2);
+        if (rc) return rc;
+    }
+    PC_CUDA(c, cudaEventRecord(st.computed, lks));
+    rc = track_chain_enqueue(c, st, frame_id, st.is_halo, batch.cap);     // fused Track (no-op unless enabled)
+    if (rc) return rc;
+    // results -> pinned host, on the download stream
+    PC_CUDA(c, cudaStreamWaitEvent(c->d2h, st.computed, 0));
+    PC_CUDA(c, cudaMemcpyAsync(st.counts_host, f->n_kps, sizeof(int) * 3, cudaMemcpyDeviceToHost, c->d2h));
+    st.rows_downloaded = false;
+    if (c->download_hint && st.rows_bytes <= kSlabCopyMax && batch.cap <= c->lim.max_features) {
+        // the caller has been taking rows: send the whole slab (counts + rows) and the keypoints now,
+        // so the pop of this frame is a single wait
+        PC_CUDA(c, cudaMemcpyAsync(st.rows_host, st.rows_dev, np > 0 ? st.rows_bytes : 128, cudaMemcpyDeviceToHost, c->d2h));
+        PC_CUDA(c, cudaMemcpyAsync(st.kps_host, f->kps, sizeof(float) * 2 * batch.cap, cudaMemcpyDeviceToHost, c->d2h));
+        st.rows_downloaded = true;
+    } else if (np > 0) {
+        PC_CUDA(c, cudaMemcpyAsync(st.rows_host, st.rows_dev, sizeof(int) * 8, cudaMemcpyDeviceToHost, c->d2h));
+    }
+    PC_CUDA(c, cudaEventRecord(st.downloaded, c->d2h));
     return PC_OK;
 }
 
@@ -766,59 +892,14 @@ int pc_analyze_push_frame(pc_ctx* c, int32_t frame_id, const uint8_t* rgb, size_
         rc = run_detector(c, f, &c->gopts, c->compute);
         if (rc) return rc;
     }
-    // every pair whose later frame is this one: (j-d -> j) and (j -> j-d), d in {1,2,4,8}
-    LKBatch batch{};
-    batch.cap = c->lim.max_features;
-    if (c->gopts.max_corners > 0) batch.cap = std::min(batch.cap, c->gopts.max_corners);
-    static const int kSkips[4] = {1, 2, 4, 8};   // |image_skips|, opticalflow.cc:76-77
-    int np = 0;
-    const bool is_halo = c->pushed_count < c->halo_frames;
+    st.is_halo = c->pushed_count < c->halo_frames;
     c->pushed_count++;
-    for (int k = 0; k < 4 && !is_halo; k++) {
-        const int32_t other = frame_id - kSkips[k];
-        if (other < first) continue;
-        FrameSlot* o = find_slot(c, other);
-        if (!o) return fail(c, PC_ERR_STATE, "frame " + std::to_string(other) + " fell out of the ring");
-        st.from[np] = other; st.to[np] = frame_id;
-        fill_pair(c, batch.pair[np], *o, *f, np, st.dev[np]);
-        np++;
-        st.from[np] = frame_id; st.to[np] = other;
-        fill_pair(c, batch.pair[np], *f, *o, np, st.dev[np]);
-        np++;
-    }
-    // presets may exceed max_corners
-    for (int k = 0; k < np; k++) {
-        const FrameSlot* src = find_slot(c, st.from[k]);
-        if (src->n_kps_host > batch.cap) batch.cap = src->n_kps_host;
-    }
-    batch.num_pairs = np;
-    st.num_pairs = np;
-    if (np > 0) {
-        const LKParams p = make_lk_params(&c->fopts);
-        span_begin(c, KF_LK, c->compute);
-        launch_lk(batch, p, c->compute);
-        span_end(c, c->compute);
-        span_begin(c, KF_COMPACT, c->compute);
-        launch_lk_compact(batch, c->compute);
-        span_end(c, c->compute);
-        rc = check_launch(c, "lk batch", 2);
-        if (rc) return rc;
-    }
-    PC_CUDA(c, cudaEventRecord(st.computed, c->compute));
-    rc = track_chain_enqueue(c, st, frame_id, is_halo, batch.cap);     // fused Track (no-op unless enabled)
-    if (rc) return rc;
-    // results -> pinned host, on the download stream
-    PC_CUDA(c, cudaStreamWaitEvent(c->d2h, st.computed, 0));
-    PC_CUDA(c, cudaMemcpyAsync(st.counts_host, f->n_kps, sizeof(int) * 3, cudaMemcpyDeviceToHost, c->d2h));
-    for (int k = 0; k < np; k++)
-        PC_CUDA(c, cudaMemcpyAsync(st.host[k].count, st.dev[k].count, sizeof(int), cudaMemcpyDeviceToHost, c->d2h));
-    PC_CUDA(c, cudaEventRecord(st.downloaded, c->d2h));
     st.busy = true;
     c->inflight.push_back(si);
     c->next_stage = (si + 1) % (int)c->stages.size();
     c->last_pushed = frame_id;
     c->any_pushed = true;
-    return PC_OK;
+    return enqueue_lk(c, st, f);
 }
 
 int pc_analyze_pop(pc_ctx* c, pc_frame_result* out, int download) {
@@ -838,20 +919,27 @@ int pc_analyze_pop(pc_ctx* c, pc_frame_result* out, int download) {
     out->num_pairs = st.num_pairs;
     FrameSlot* f = find_slot(c, st.frame_id);
     if (f) f->n_kps_host = n_kps;
-    if (download) {
-        // second, size-exact download (counts are known now)
+    c->download_hint = download != 0;
+    if (download && !st.rows_downloaded) {
+        // second phase (the counts are known now), on its own stream: c->d2h already holds the count
+        // downloads of the frames pushed after this one, which wait for their LK batches
+        cudaStream_t s = c->d2h_rows;
         if (f && n_kps > 0)
-            PC_CUDA(c, cudaMemcpyAsync(st.kps_host, f->kps, sizeof(float) * 2 * n_kps, cudaMemcpyDeviceToHost, c->d2h));
-        for (int k = 0; k < st.num_pairs; k++) {
-            const int n = *st.host[k].count;
-            if (n <= 0) continue;
-            PC_CUDA(c, cudaMemcpyAsync(st.host[k].idx, st.dev[k].idx, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, c->d2h));
-            PC_CUDA(c, cudaMemcpyAsync(st.host[k].tgt, st.dev[k].tgt, sizeof(float) * 2 * n, cudaMemcpyDeviceToHost, c->d2h));
-            PC_CUDA(c, cudaMemcpyAsync(st.host[k].err, st.dev[k].err, sizeof(float) * n, cudaMemcpyDeviceToHost, c->d2h));
+            PC_CUDA(c, cudaMemcpyAsync(st.kps_host, f->kps, sizeof(float) * 2 * n_kps, cudaMemcpyDeviceToHost, s));
+        if (st.num_pairs > 0 && st.rows_bytes <= kSlabCopyMax) {
+            PC_CUDA(c, cudaMemcpyAsync(st.rows_host + 128, st.rows_dev + 128, st.rows_bytes - 128, cudaMemcpyDeviceToHost, s));
+        } else {
+            for (int k = 0; k < st.num_pairs; k++) {
+                const int n = *st.host[k].count;
+                if (n <= 0) continue;
+                PC_CUDA(c, cudaMemcpyAsync(st.host[k].idx, st.dev[k].idx, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, s));
+                PC_CUDA(c, cudaMemcpyAsync(st.host[k].tgt, st.dev[k].tgt, sizeof(float) * 2 * n, cudaMemcpyDeviceToHost, s));
+                PC_CUDA(c, cudaMemcpyAsync(st.host[k].err, st.dev[k].err, sizeof(float) * n, cudaMemcpyDeviceToHost, s));
+            }
         }
-        PC_CUDA(c, cudaStreamSynchronize(c->d2h));
-        out->keypoints = st.kps_host;
+        PC_CUDA(c, cudaStreamSynchronize(s));
     }
+    if (download) out->keypoints = st.kps_host;
     for (int k = 0; k < st.num_pairs; k++) {
         pc_pair_rows& r = out->pairs[k];
         r.image_id_from = st.from[k];

@@ -47,13 +47,20 @@ struct PairOut {              // compacted LK rows of one pair (device) + pinned
 struct Stage {                // one in-flight frame of the streaming analyzer
     uint8_t* rgb_dev = nullptr;       // staging for host-provided frames
     size_t rgb_bytes = 0;
-    PairOut dev[8], host[8];
+    PairOut dev[8], host[8];          // views into the two slabs below
+    // One device slab and one pinned mirror per stage: [8 row counts | pair 0: idx, tgt, err | pair 1 ...],
+    // so a frame's result travels in one copy (capi.cu: alloc_stage_rows).
+    uint8_t* rows_dev = nullptr;
+    uint8_t* rows_host = nullptr;
+    size_t rows_bytes = 0;
+    bool rows_downloaded = false;     // the row slab + keypoints were queued with the counts (single-phase pop)
     int32_t from[8], to[8];
     int num_pairs = 0;
     float* kps_host = nullptr;        // pinned
     int* counts_host = nullptr;       // pinned: [0]=n_kps [1]=n_accepted [2]=greedy_remaining
     int32_t frame_id = 0;
-    cudaEvent_t uploaded = nullptr, gray_done = nullptr, computed = nullptr, downloaded = nullptr;
+    cudaEvent_t uploaded = nullptr, gray_done = nullptr, detected = nullptr, computed = nullptr, downloaded = nullptr;
+    bool is_halo = false;
     bool busy = false;
     bool gray_pending = false;
     // fused analyze -> track chain (track.cu): this frame's pose solve
@@ -94,6 +101,11 @@ struct pc_ctx {
     int device = 0;
     int sm_count = 0;
     cudaStream_t compute = nullptr, h2d = nullptr, d2h = nullptr;
+    cudaStream_t d2h_rows = nullptr;     // pop-time row downloads: never queued behind a later frame's counts
+    bool download_hint = false;          // the last pop asked for rows: queue the next frames' rows with their counts
+    // streaming analyzer: LK batches run on this low-priority stream next to the following frame's
+    // pyramid + detector on `compute` (nullptr = everything on `compute`)
+    cudaStream_t side = nullptr;
     std::string err;
     uint64_t launches = 0;
     uint64_t stamp = 0;
@@ -122,7 +134,7 @@ struct pc_ctx {
     int next_stage = 0;
     int32_t last_pushed = 0; bool any_pushed = false;
     int halo_frames = 0, pushed_count = 0;
-    cudaEvent_t marks[8] = {nullptr}; cudaEvent_t join_a = nullptr, join_b = nullptr;
+    cudaEvent_t marks[8] = {nullptr}; cudaEvent_t join_a = nullptr, join_b = nullptr, join_c = nullptr;
     std::unordered_map<int32_t, std::vector<float>> preset_kps;
 
     // synthetic texture

@@ -142,26 +142,44 @@ struct PadPlanes {
     int w[kMaxLevels], h[kMaxLevels], pitch[kMaxLevels];
 };
 
+// Work items of a plane: the top and bottom bands as aligned 4-byte words (corners included), then
+// the left and right bands as one 16-byte run per row and side.  data is 16-byte aligned and the
+// pitch a multiple of 128, so every store is a full aligned word.
 __global__ void __launch_bounds__(256) pad_border_kernel(PadPlanes P) {
     const int L = blockIdx.y;
     const int w = P.w[L], h = P.h[L], pitch = P.pitch[L];
     uint8_t* img = P.data[L];
-    const int full_w = w + 2 * kPadX;
-    const int n_rows = 2 * kPadY * full_w;                 // top + bottom bands (with corners)
-    const int n_cols = 2 * kPadX * h;                      // left + right bands
+    const int words = (w + 2 * kPadX + 3) / 4;             // per band row, from x = -kPadX
+    const int n_rows = 2 * kPadY * words;
+    const int n_cols = 2 * h;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_rows + n_cols; i += gridDim.x * blockDim.x) {
-        int x, y;
         if (i < n_rows) {
-            const int r = i / full_w;
-            x = i - r * full_w - kPadX;
-            y = r < kPadY ? r - kPadY : h + (r - kPadY);
+            const int r = i / words;
+            const int x0 = (i - r * words) * 4 - kPadX;
+            const int y = r < kPadY ? r - kPadY : h + (r - kPadY);
+            const uint8_t* src = img + (ptrdiff_t)reflect101(y, h) * pitch;
+            uint32_t v = 0;
+#pragma unroll
+            for (int k = 0; k < 4; k++) v |= (uint32_t)src[reflect101(x0 + k, w)] << (8 * k);
+            *reinterpret_cast<uint32_t*>(img + (ptrdiff_t)y * pitch + x0) = v;
         } else {
             const int j = i - n_rows;
-            y = j / (2 * kPadX);
-            const int c = j - y * (2 * kPadX);
-            x = c < kPadX ? c - kPadX : w + (c - kPadX);
+            const int y = j >> 1;
+            uint8_t* row = img + (ptrdiff_t)y * pitch;
+            if (j & 1) {                                    // right band: x = w .. w+15 (bytes, w need not be aligned)
+#pragma unroll
+                for (int k = 0; k < kPadX; k++) row[w + k] = row[reflect101(w + k, w)];
+            } else {                                        // left band: x = -16 .. -1
+                uint32_t q[4];
+#pragma unroll
+                for (int g = 0; g < 4; g++) {
+                    q[g] = 0;
+#pragma unroll
+                    for (int k = 0; k < 4; k++) q[g] |= (uint32_t)row[reflect101(-kPadX + 4 * g + k, w)] << (8 * k);
+                }
+                *reinterpret_cast<uint4*>(row - kPadX) = make_uint4(q[0], q[1], q[2], q[3]);
+            }
         }
-        img[(ptrdiff_t)y * pitch + x] = img[(ptrdiff_t)reflect101(y, h) * pitch + reflect101(x, w)];
     }
 }
 
@@ -170,7 +188,7 @@ void launch_pad_border(const Image8* planes, int levels, cudaStream_t s) {
     int most = 0;
     for (int L = 0; L < levels; L++) {
         P.data[L] = planes[L].data; P.w[L] = planes[L].w; P.h[L] = planes[L].h; P.pitch[L] = planes[L].pitch;
-        most = std::max(most, 2 * kPadY * (planes[L].w + 2 * kPadX) + 2 * kPadX * planes[L].h);
+        most = std::max(most, 2 * kPadY * ((planes[L].w + 2 * kPadX + 3) / 4) + 2 * planes[L].h);
     }
     dim3 grid(std::min((most + 255) / 256, 296), levels);
     pad_border_kernel<<<grid, 256, 0, s>>>(P);

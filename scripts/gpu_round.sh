@@ -7,14 +7,16 @@ OUT=gpurun_out
 mkdir -p $OUT
 nvidia-smi -L; nproc
 timeout 600 python -m pytest tests -x -q -m gpu 2>&1 | tail -15 | tee $OUT/${TAG}_tests.log
-timeout 600 python bench.py --steps 10 --warmup 3 > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err
+timeout 600 python bench.py --steps 10 --warmup 3 --diag > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err
 cat $OUT/${TAG}_bench.json; tail -5 $OUT/${TAG}_bench.err
-timeout 300 python bench.py --steps 10 --warmup 3 --no-track --no-cpu-baseline > $OUT/${TAG}_bench_notrack.json 2>> $OUT/${TAG}_bench.err
-cat $OUT/${TAG}_bench_notrack.json
+PC_LK_STREAM=0 timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_bench_1stream.json 2>> $OUT/${TAG}_bench.err
+cat $OUT/${TAG}_bench_1stream.json
+if [ -n "$KERNELS" ] && [ "$KERNELS" != "none" ]; then
 # launch list of the bench command (cold-cache, serialised: shares only)
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file $OUT/${TAG}_launches.csv \
     python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu-baseline > $OUT/${TAG}_ncu_b.log 2>&1
 # one full capture of the named kernels (skip the warm-up launches)
-timeout 900 ncu --set full --clock-control none --import-source on -k "regex:$KERNELS" -s 40 -c 6 \
+timeout 900 ncu --set full --clock-control none --import-source on -k "regex:$KERNELS" -s 40 -c 8 \
     -o $OUT/${TAG}_prof -f python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu-baseline > $OUT/${TAG}_ncu_full.log 2>&1
-ls -la $OUT
+fi
+ls -la $OUT | tail -8
