@@ -159,7 +159,7 @@ static int run_detector(pc_ctx* c, FrameSlot* f, const pc_gftt_opts* go, cudaStr
     g.block_h = (f->h + g.grid_rows - 1) / g.grid_rows;   // gftt.cc:42-43
     g.block_w = (f->w + g.grid_cols - 1) / g.grid_cols;
     span_begin(c, KF_MIN_EIG, s);
-    launch_min_eig(f->level[0], c->eig, c->eig_pitch, g, c->cell_max, s);
+    launch_min_eig(f->level[0], c->eig, c->eig_pitch, g, c->cell_max, c->det_zero, c->det_zero_ints, f->n_kps, s);
     span_end(c, s);
     span_begin(c, KF_SELECT, s);
     launch_nms_candidates(c->eig, c->eig_pitch, f->w, f->h, g, c->cell_max, go->quality_level, c->state,
@@ -273,9 +273,8 @@ pc_ctx::~pc_ctx() {
         cudaFree(s.base);
         cudaFree(s.kps); cudaFree(s.n_kps);
     }
-    cudaFree(eig); cudaFree(state); cudaFree(cell_max); cudaFree(cand); cudaFree(cand_count);
-    cudaFree(sel.accepted); cudaFree(sel.sorted); cudaFree(sel.round_counters); cudaFree(sel.cub_temp);
-    cudaFree(sel.strong); cudaFree(sel.kept_hist); cudaFree(sel.hist); cudaFree(sel.sel);
+    cudaFree(eig); cudaFree(state); cudaFree(cell_max); cudaFree(cand); cudaFree(det_zero);
+    cudaFree(sel.accepted); cudaFree(sel.sorted); cudaFree(sel.cub_temp); cudaFree(sel.strong);
     cudaFree(lk_next); cudaFree(lk_status); cudaFree(lk_err);
     free_pair_out(sync_out, false);
     cudaFree(rgb_scratch);
@@ -417,18 +416,23 @@ int pc_create(const pc_limits* limits, pc_ctx** out) {
     // 3x3 NMS leaves at most one candidate per 2x2 block except on plateaus; w*h/4 is ample
     cp->cand_cap = std::max(1024, (int)(((size_t)W * H) / 4));
     PC_CUDA(nullptr, cudaMalloc(&cp->cand, sizeof(unsigned long long) * cp->cand_cap));
-    PC_CUDA(nullptr, cudaMalloc(&cp->cand_count, sizeof(int)));
+    // one block holds every detector counter that must be zero at the start of a frame, so the init
+    // launch of the min-eig stage clears them all: [0] candidate count, [8..15] select scratch,
+    // then the greedy round counters and the two 4096-bin value histograms
+    cp->det_zero_ints = 16 + 2 * kMaxGreedyRounds + 2 * 4096;
+    PC_CUDA(nullptr, cudaMalloc(&cp->det_zero, sizeof(int) * cp->det_zero_ints));
+    PC_CUDA(nullptr, cudaMemset(cp->det_zero, 0, sizeof(int) * cp->det_zero_ints));
+    cp->cand_count = cp->det_zero;
     cp->sel.cap = cp->cand_cap;
     PC_CUDA(nullptr, cudaMalloc(&cp->sel.accepted, sizeof(unsigned long long) * cp->cand_cap));
     cp->sel.sorted_cap = 1;
     while (cp->sel.sorted_cap < cp->cand_cap) cp->sel.sorted_cap <<= 1;
     PC_CUDA(nullptr, cudaMalloc(&cp->sel.sorted, sizeof(unsigned long long) * cp->sel.sorted_cap));
-    PC_CUDA(nullptr, cudaMalloc(&cp->sel.round_counters, sizeof(int) * 2 * kMaxGreedyRounds));
+    cp->sel.sel = cp->det_zero + 8;
+    cp->sel.round_counters = cp->det_zero + 16;
+    cp->sel.hist = cp->sel.round_counters + 2 * kMaxGreedyRounds;
+    cp->sel.kept_hist = cp->sel.hist + 4096;
     PC_CUDA(nullptr, cudaMalloc(&cp->sel.strong, sizeof(unsigned long long) * cp->cand_cap));
-    PC_CUDA(nullptr, cudaMalloc(&cp->sel.hist, sizeof(int) * 4096));
-    PC_CUDA(nullptr, cudaMalloc(&cp->sel.kept_hist, sizeof(int) * 65536));
-    PC_CUDA(nullptr, cudaMemset(cp->sel.kept_hist, 0, sizeof(int) * 65536));
-    PC_CUDA(nullptr, cudaMalloc(&cp->sel.sel, sizeof(int) * 8));
     cp->sel.cub_temp_bytes = select_cub_temp_bytes(cp->cand_cap);
     PC_CUDA(nullptr, cudaMalloc(&cp->sel.cub_temp, cp->sel.cub_temp_bytes));
     PC_CUDA(nullptr, cudaMalloc(&cp->lk_next, sizeof(float) * 2 * (size_t)cap * 8));
@@ -581,7 +585,7 @@ int pc_min_eig_map(pc_ctx* c, int32_t frame_id, float* eig_out, size_t cap_float
     if (cap_floats < (size_t)f->w * f->h) return fail(c, PC_ERR_CAPACITY, "eig output buffer too small");
     DetectGrid g{1, 1, f->w, f->h};
     span_begin(c, KF_MIN_EIG, c->compute);
-    launch_min_eig(f->level[0], c->eig, c->eig_pitch, g, c->cell_max, c->compute);
+    launch_min_eig(f->level[0], c->eig, c->eig_pitch, g, c->cell_max, c->det_zero, c->det_zero_ints, nullptr, c->compute);
     span_end(c, c->compute);
     int rc = check_launch(c, "min_eig", 2);
     if (rc) return rc;

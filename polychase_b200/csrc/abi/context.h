@@ -117,6 +117,7 @@ struct pc_ctx {
     uint8_t* state = nullptr; int state_pitch = 0;
     int* cell_max = nullptr; int cell_cap = 0;
     unsigned long long* cand = nullptr; int cand_cap = 0; int* cand_count = nullptr;
+    int* det_zero = nullptr; int det_zero_ints = 0;   // counter block cleared at the start of every detector run
     pc::SelectWorkspace sel{};
 
     // LK dense scratch: [8][cap]

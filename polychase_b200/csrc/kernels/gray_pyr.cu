@@ -167,8 +167,11 @@ __global__ void __launch_bounds__(256) pad_border_kernel(PadPlanes P) {
             const int y = j >> 1;
             uint8_t* row = img + (ptrdiff_t)y * pitch;
             if (j & 1) {                                    // right band: x = w .. w+15 (bytes, w need not be aligned)
+                uint8_t v[kPadX];                           // all loads first: the stores may alias them for the compiler
 #pragma unroll
-                for (int k = 0; k < kPadX; k++) row[w + k] = row[reflect101(w + k, w)];
+                for (int k = 0; k < kPadX; k++) v[k] = row[reflect101(w + k, w)];
+#pragma unroll
+                for (int k = 0; k < kPadX; k++) row[w + k] = v[k];
             } else {                                        // left band: x = -16 .. -1
                 uint32_t q[4];
 #pragma unroll

@@ -38,9 +38,14 @@ struct DetectGrid {
     int grid_rows, grid_cols, block_w, block_h;   // gftt.cc:39-43
 };
 // eig: w*h floats (pitch in floats = eig_pitch); cell_max: grid_rows*grid_cols ordered ints
-void launch_min_eig(Image8 gray, float* eig, int eig_pitch, DetectGrid g, int* cell_max, cudaStream_t s);
+// Also clears the detector's counter block (`zero_block`, `zero_ints` ints: candidate count, value
+// histograms, greedy round counters, select scratch) and the frame's three counters
+// (`frame_counters`: n_kps, n_accepted, greedy_remaining) in its init launch: K5..K7 rely on that.
+void launch_min_eig(Image8 gray, float* eig, int eig_pitch, DetectGrid g, int* cell_max, int* zero_block,
+                    int zero_ints, int* frame_counters, cudaStream_t s);
 // candidates: 64-bit keys (ordered value << 32 | address); state: u8 map (pitch = gray.pitch)
-// value_hist: 4096 bins over the top 12 bits of the ordered candidate value (cleared here)
+// value_hist: 4096 bins over the top 12 bits of the ordered candidate value; it and cand_count are
+// zero on entry (launch_min_eig)
 void launch_nms_candidates(const float* eig, int eig_pitch, int w, int h, DetectGrid g,
                            const int* cell_max, double quality_level, uint8_t* state, int state_pitch,
                            unsigned long long* cand, int cand_cap, int* cand_count, int* value_hist,
@@ -55,8 +60,8 @@ struct SelectWorkspace {
     int* round_counters;               // 2 * kMaxGreedyRounds ints
     int* remaining;                    // device int: undecided candidates left (0 = converged)
     int* hist;                         // 4096 ints: 12-bit value histogram of all candidates (written by K5)
-    int* kept_hist;                    // 65536 ints: 16-bit value histogram of kept keys; zero between frames
-    int* sel;                          // small device scratch: [1] strong count
+    int* kept_hist;                    // 4096 ints: 12-bit value histogram of kept keys
+    int* sel;                          // 8 ints: [1] strong count, [2] threshold bin, [3] short-list size, [4] its fill cursor
     void* cub_temp; size_t cub_temp_bytes;
     int cap;
     int sorted_cap;

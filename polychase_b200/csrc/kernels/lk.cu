@@ -281,40 +281,55 @@ __global__ void __launch_bounds__(LK_WARPS * 32) lk_kernel(LKBatch batch, LKPara
     }
 }
 
-// K9: order-preserving compaction of status==1 rows (one block per pair).
+// K9: order-preserving compaction of status==1 rows (one block per pair).  A thread owns
+// CP_PER consecutive rows of each 1024 * CP_PER chunk: one warp-shuffle scan + one shared-memory
+// pass over the 32 warp totals per chunk.
+constexpr int CP_PER = 8;
 __global__ void __launch_bounds__(1024) lk_compact_kernel(LKBatch batch) {
     const LKPair& pr = batch.pair[blockIdx.x];
-    __shared__ int warp_tot[32];
-    __shared__ int base_s;
+    __shared__ int warp_tot[2][32];
     const int n = min(*pr.n_pts, batch.cap);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    if (threadIdx.x == 0) base_s = 0;
-    __syncthreads();
-    for (int start = 0; start < n; start += 1024) {
-        const int i = start + threadIdx.x;
-        const bool keep = i < n && pr.status[i] == 1;
-        const unsigned m = __ballot_sync(0xffffffffu, keep);
-        if (lane == 0) warp_tot[wid] = __popc(m);
-        __syncthreads();
-        int off = 0;
-        for (int k = 0; k < wid; k++) off += warp_tot[k];
-        const int base = base_s;
-        if (keep) {
-            const int slot = base + off + __popc(m & ((1u << lane) - 1));
-            pr.out_idx[slot] = (uint32_t)i;
-            pr.out_tgt[2 * slot] = pr.next[2 * i];
-            pr.out_tgt[2 * slot + 1] = pr.next[2 * i + 1];
-            pr.out_err[slot] = pr.err[i];
+    int base = 0, buf = 0;
+    for (int start = 0; start < n; start += 1024 * CP_PER, buf ^= 1) {
+        const int i0 = start + threadIdx.x * CP_PER;
+        unsigned keep = 0;
+#pragma unroll
+        for (int k = 0; k < CP_PER; k++)
+            if (i0 + k < n && pr.status[i0 + k] == 1) keep |= 1u << k;
+        const int mine = __popc(keep);
+        int incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
         }
+        if (lane == 31) warp_tot[buf][wid] = incl;
         __syncthreads();
-        if (threadIdx.x == 0) {
-            int tot = 0;
-            for (int k = 0; k < 32; k++) tot += warp_tot[k];
-            base_s = base + tot;
+        const int wt = warp_tot[buf][lane];                  // 32 warps: one total per lane
+        int wincl = wt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, wincl, o);
+            if (lane >= o) wincl += v;
         }
-        __syncthreads();
+        const int before = __shfl_sync(0xffffffffu, wincl - wt, wid);
+        const int total = __shfl_sync(0xffffffffu, wincl, 31);
+        int slot = base + before + incl - mine;
+#pragma unroll
+        for (int k = 0; k < CP_PER; k++) {
+            if (keep & (1u << k)) {
+                const int i = i0 + k;
+                const float2 t = *reinterpret_cast<const float2*>(pr.next + 2 * i);
+                pr.out_idx[slot] = (uint32_t)i;
+                *reinterpret_cast<float2*>(pr.out_tgt + 2 * slot) = t;
+                pr.out_err[slot] = pr.err[i];
+                slot++;
+            }
+        }
+        base += total;
     }
-    if (threadIdx.x == 0) *pr.out_count = base_s;
+    if (threadIdx.x == 0) *pr.out_count = base;
 }
 
 template <int WIN>

@@ -25,6 +25,8 @@
 //     warp takes only when one of its keypoints' patches leaves the image at that level.
 // Integer stages are exact and float stages use explicit-rounding intrinsics (file is compiled
 // with -fmad=false), so results are bit-identical to the oracle (tests/test_gpu_analyze.py).
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -366,10 +368,27 @@ __global__ void __launch_bounds__(LK_WARPS * 32, 4) lk10_kernel(LKBatch batch, L
 
 }  // namespace
 
+// The kernel needs the whole register file at 4 blocks per SM.  PC_LK_BLOCKS_PER_SM = 1..3 caps its
+// residency (through an unused dynamic shared memory reservation) so that the kernels of the next
+// frame's detector, queued on another stream, find room next to it.
+static int lk10_smem_reservation() {
+    static int bytes = -1;
+    if (bytes < 0) {
+        bytes = 0;
+        const char* e = getenv("PC_LK_BLOCKS_PER_SM");
+        const int n = e ? atoi(e) : 0;
+        if (n >= 1 && n <= 3) {
+            bytes = (200 * 1024 / n) & ~1023;
+            cudaFuncSetAttribute(lk10_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+        }
+    }
+    return bytes;
+}
+
 void launch_lk10(const LKBatch& batch, const LKParams& p, cudaStream_t s) {
     const int per_block = LK_WARPS * PTS_PER_WARP;
     dim3 grid((batch.cap + per_block - 1) / per_block, batch.num_pairs);
-    lk10_kernel<<<grid, LK_WARPS * 32, 0, s>>>(batch, p);
+    lk10_kernel<<<grid, LK_WARPS * 32, lk10_smem_reservation(), s>>>(batch, p);
 }
 
 }  // namespace pc

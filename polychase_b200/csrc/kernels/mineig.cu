@@ -224,15 +224,19 @@ min_eig_kernel(const uint8_t* __restrict__ gray, int w, int h, int pitch, float*
     }
 }
 
-__global__ void init_cell_max_kernel(int* cell_max, int n, int* counters, int n_counters) {
+__global__ void init_cell_max_kernel(int* cell_max, int n, int* counters, int n_counters, int* frame_counters) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) cell_max[i] = 0x80000000;
     if (i < n_counters) counters[i] = 0;
+    if (frame_counters && i < 3) frame_counters[i] = 0;
 }
 
-void launch_min_eig(Image8 gray, float* eig, int eig_pitch, DetectGrid g, int* cell_max, cudaStream_t s) {
+void launch_min_eig(Image8 gray, float* eig, int eig_pitch, DetectGrid g, int* cell_max, int* zero_block,
+                    int zero_ints, int* frame_counters, cudaStream_t s) {
     const int ncell = g.grid_rows * g.grid_cols;
-    init_cell_max_kernel<<<(ncell + 255) / 256, 256, 0, s>>>(cell_max, ncell, nullptr, 0);
+    const int n_init = std::max(std::max(ncell, zero_block ? zero_ints : 0), 3);
+    init_cell_max_kernel<<<(n_init + 255) / 256, 256, 0, s>>>(cell_max, ncell, zero_block, zero_block ? zero_ints : 0,
+                                                              frame_counters);
     const int tiles_x = (gray.w + ME_COLS - 1) / ME_COLS, tiles_y = (gray.h + ME_ROWS - 1) / ME_ROWS;
     const int blocks = (tiles_x * tiles_y + ME_WARPS - 1) / ME_WARPS;
     min_eig_kernel<<<blocks, ME_WARPS * 32, 0, s>>>(gray.data, gray.w, gray.h, gray.pitch, eig, eig_pitch, g, cell_max,
@@ -393,8 +397,6 @@ __global__ void __launch_bounds__(NMS_WARPS * 32) nms_candidates_kernel(
 void launch_nms_candidates(const float* eig, int eig_pitch, int w, int h, DetectGrid g, const int* cell_max,
                            double quality_level, uint8_t* state, int state_pitch, unsigned long long* cand,
                            int cand_cap, int* cand_count, int* value_hist, cudaStream_t s) {
-    cudaMemsetAsync(cand_count, 0, sizeof(int), s);
-    cudaMemsetAsync(value_hist, 0, sizeof(int) * 4096, s);
     const int tiles_x = (w + 127) / 128, tiles_y = (h + NMS_ROWS - 1) / NMS_ROWS;
     int blocks = (tiles_x * tiles_y + NMS_WARPS - 1) / NMS_WARPS;
     static int sm_count = 0;

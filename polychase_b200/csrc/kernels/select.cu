@@ -17,10 +17,11 @@
 // i.e. it returns a prefix of the unlimited result.  Because decisions only depend on stronger
 // candidates, the fixed point is first run on the strongest ~4*max_corners candidates (a value
 // threshold from a 12-bit histogram); only if that yields fewer than max_corners kept corners
-// does a second pass process everything.  Kept keys are counted into a 16-bit-bin histogram
-// of their value as they are accepted; the final kernel finds the bin that holds the
-// max_corners-th strongest key, gathers the keys at or above it into shared memory and ranks
-// them by counting ((value, address) descending): rank r < max_corners is keypoint r.
+// does a second pass process everything.  Kept keys are counted into a 12-bit-bin histogram
+// of their value as they are accepted; compact_top_kernel finds the bin that holds the
+// max_corners-th strongest key and gathers the keys at or above it (max_corners plus part of one
+// bin); select_rank_emit_kernel stages that short list in shared memory and ranks it by counting
+// ((value, address) descending): rank r < max_corners is keypoint r.
 // With max_corners == 0 every kept key is sorted (CUB radix sort).
 #include <cooperative_groups.h>
 #include <cub/device/device_radix_sort.cuh>
@@ -162,7 +163,7 @@ __global__ void __launch_bounds__(256) greedy_suppress_kernel(
             } else if (d == ST_KEPT) {
                 *(volatile uint8_t*)sp = ST_KEPT;
                 accepted[atomicAdd(accepted_count, 1)] = key;
-                if (kept_hist) atomicAdd(&kept_hist[(unsigned)(key >> 48)], 1);
+                if (kept_hist) atomicAdd(&kept_hist[(unsigned)(key >> 52)], 1);
             } else {
                 undecided++;
             }
@@ -184,7 +185,7 @@ __global__ void accept_all_kernel(const unsigned long long* __restrict__ cand, c
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const unsigned long long key = cand[i];
         accepted[i] = key;
-        if (kept_hist) atomicAdd(&kept_hist[(unsigned)(key >> 48)], 1);
+        if (kept_hist) atomicAdd(&kept_hist[(unsigned)(key >> 52)], 1);
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) { *accepted_count = n; *remaining = 0; }
 }
@@ -276,70 +277,77 @@ __global__ void __launch_bounds__(256) compact_strong_kernel(const unsigned long
 }
 
 // ---- final selection: the max_corners strongest kept keys, in order, as keypoints -------------
-// Every CTA finds the 16-bit value bin that holds the k-th strongest kept key (k = min(max_corners,
-// kept)), gathers the m >= k keys at or above it into shared memory, and ranks its own share of
-// them by counting (rank = number of gathered keys that are larger; keys are unique), one warp per
-// key.  rank < k -> keypoint slot `rank`.  m is k plus the population of one fine bin, so the m^2
-// comparisons spread over the grid are a few microseconds, where a single-CTA sort was ~130 us.
+// compact_top_kernel: every CTA finds the 12-bit value bin that holds the k-th strongest kept key
+// (k = min(max_corners, kept); 16 KB histogram, recomputed per CTA) and appends its share of the keys
+// at or above that bin to `top` (m >= k of them: k plus part of one bin's population).
+// select_rank_emit_kernel: every CTA stages top[0..m) in shared memory and ranks its share by
+// counting (rank = number of keys that are larger; keys are unique), one warp per key:
+// rank < k -> keypoint slot `rank`.  The m^2 comparisons spread over the grid are a few
+// microseconds, where a single-CTA sort was ~130 us.
 constexpr int RANK_THREADS = 1024;
 constexpr int RANK_SMEM_KEYS = 16384;                       // 128 KB of dynamic shared memory
 
-// One CTA scans the 65536-bin histogram of kept keys once per frame (sel[2] = threshold bin,
-// sel[3] = number of keys at or above it); the ranking CTAs only read those two ints.
-__global__ void __launch_bounds__(RANK_THREADS) rank_threshold_kernel(const int* __restrict__ accepted_count,
-                                                                      const int* __restrict__ kept_hist,
-                                                                      int max_corners, int kps_cap,
-                                                                      int* __restrict__ sel) {
-    __shared__ int s_warp[RANK_THREADS / 32], s_res[8];
-    const int k = min(min(max_corners, *accepted_count), kps_cap);
-    int m = 0, thr = 0;
-    if (k > 0) thr = suffix_threshold_bin<RANK_THREADS, 64>(kept_hist, k, s_warp, s_res, &m);
-    if (threadIdx.x == 0) { sel[2] = thr; sel[3] = m; }
+// sel[2] = threshold bin, sel[3] = m, sel[4] = fill cursor of top[] (zero on entry)
+__global__ void __launch_bounds__(256) compact_top_kernel(const unsigned long long* __restrict__ accepted,
+                                                          const int* __restrict__ accepted_count,
+                                                          const int* __restrict__ kept_hist, int max_corners,
+                                                          int kps_cap, unsigned long long* __restrict__ top,
+                                                          int* __restrict__ sel, int* __restrict__ kps_count) {
+    __shared__ int s_warp[8], s_res[8];
+    const int n = *accepted_count;
+    const int k = min(min(max_corners, n), kps_cap);
+    if (blockIdx.x == 0 && threadIdx.x == 0) *kps_count = k;
+    if (k == 0) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) { sel[2] = 0; sel[3] = 0; }
+        return;
+    }
+    int m = 0;
+    const unsigned thr = (unsigned)suffix_threshold_bin<256, 16>(kept_hist, k, s_warp, s_res, &m);
+    if (blockIdx.x == 0 && threadIdx.x == 0) { sel[2] = (int)thr; sel[3] = m; }
+    const int lane = threadIdx.x & 31;
+    for (int base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
+        const int i = base + threadIdx.x;
+        unsigned long long key = 0ull;
+        bool keep = false;
+        if (i < n) {
+            key = accepted[i];
+            keep = (unsigned)(key >> 52) >= thr;
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, keep);
+        if (bal) {
+            const int leader = __ffs(bal) - 1;
+            int b = 0;
+            if (lane == leader) b = atomicAdd(&sel[4], __popc(bal));
+            b = __shfl_sync(0xffffffffu, b, leader);
+            if (keep) top[b + __popc(bal & ((1u << lane) - 1))] = key;
+        }
+    }
 }
 
 __global__ void __launch_bounds__(RANK_THREADS) select_rank_emit_kernel(
-    const unsigned long long* __restrict__ accepted, const int* __restrict__ accepted_count,
-    const int* __restrict__ sel, int max_corners, int w, float* __restrict__ kps, int kps_cap,
-    int* __restrict__ kps_count) {
+    const unsigned long long* __restrict__ top, const int* __restrict__ sel, const int* __restrict__ kps_count, int w,
+    float* __restrict__ kps) {
     extern __shared__ __align__(16) unsigned long long s_keys[];
-    __shared__ int s_fill;
     const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
-    const int n = *accepted_count;
-    const int k = min(min(max_corners, n), kps_cap);
-    if (blockIdx.x == 0 && t == 0) *kps_count = k;
-    if (k == 0) return;
-    const unsigned thr = (unsigned)sel[2];
+    const int k = *kps_count;
     const int m = sel[3];
+    if (k == 0 || m == 0) return;
     const bool in_smem = m < RANK_SMEM_KEYS;
-    if (t == 0) s_fill = 0;
-    __syncthreads();
     if (in_smem) {
-        for (int base = 0; base < n; base += RANK_THREADS) {
-            const int i = base + t;
-            unsigned long long key = 0ull;
-            bool keep = false;
-            if (i < n) {
-                key = accepted[i];
-                keep = (unsigned)(key >> 48) >= thr;
-            }
-            const unsigned bal = __ballot_sync(0xffffffffu, keep);
-            if (bal) {
-                const int leader = __ffs(bal) - 1;
-                int b = 0;
-                if (lane == leader) b = atomicAdd(&s_fill, __popc(bal));
-                b = __shfl_sync(0xffffffffu, b, leader);
-                if (keep) s_keys[b + __popc(bal & ((1u << lane) - 1))] = key;
-            }
+        const ulonglong2* g2 = reinterpret_cast<const ulonglong2*>(top);
+        ulonglong2* s2 = reinterpret_cast<ulonglong2*>(s_keys);
+        for (int j = t; 2 * j + 1 < m; j += RANK_THREADS) s2[j] = g2[j];
+        if (t == 0) {
+            if (m & 1) s_keys[m - 1] = top[m - 1];
+            s_keys[m] = 0ull;                                // pad to an even count for the 16-byte loads
         }
-        if (t == 0) s_keys[m] = 0ull;                        // pad to an even count for the 16-byte loads
         __syncthreads();
     }
-    // this CTA's share of the accepted list; one warp per candidate key
-    const int per_cta = (n + gridDim.x - 1) / gridDim.x;
-    const int lo = blockIdx.x * per_cta, hi = min(lo + per_cta, n);
+    // this CTA's share of the list; one warp per key
+    const int per_cta = (m + gridDim.x - 1) / gridDim.x;
+    const int lo = blockIdx.x * per_cta, hi = min(lo + per_cta, m);
     for (int i = lo + wid; i < hi; i += RANK_THREADS / 32) {
-        const unsigned long long key = accepted[i];
-        if ((unsigned)(key >> 48) < thr) continue;          // warp-uniform
+        const unsigned long long key = in_smem ? s_keys[i] : top[i];
         int cnt = 0;
         if (in_smem) {
             const ulonglong2* s2 = reinterpret_cast<const ulonglong2*>(s_keys);
@@ -348,7 +356,7 @@ __global__ void __launch_bounds__(RANK_THREADS) select_rank_emit_kernel(
                 cnt += (q.x > key ? 1 : 0) + (q.y > key ? 1 : 0);
             }
         } else {                                             // pathological value plateau: scan the global list
-            for (int j = lane; j < n; j += 32) cnt += accepted[j] > key ? 1 : 0;
+            for (int j = lane; j < m; j += 32) cnt += top[j] > key ? 1 : 0;
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
@@ -406,19 +414,21 @@ void launch_select(const unsigned long long* cand, const int* cand_count, int ca
                    int eig_pitch, uint8_t* state, int state_pitch, int w, int h, double min_distance,
                    int max_corners, SelectWorkspace ws, float* kps_out, int kps_cap, int* kps_count, int sm_count,
                    cudaStream_t s) {
-    cudaFuncSetAttribute(select_rank_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (int)(RANK_SMEM_KEYS * sizeof(unsigned long long)));   // per device, cheap
-    cudaMemsetAsync(ws.accepted_count, 0, sizeof(int), s);
+    // accepted_count, kept_hist, round_counters and sel are zero on entry (launch_min_eig clears the
+    // detector's counter block and the frame's counters)
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(select_rank_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)(RANK_SMEM_KEYS * sizeof(unsigned long long)));
+        attr_set = true;
+    }
     const bool limited = max_corners > 0;
     int* kept_hist = limited ? ws.kept_hist : nullptr;
-    if (limited) cudaMemsetAsync(ws.kept_hist, 0, sizeof(int) * 65536, s);
     // the unlimited path sorts the whole accepted[] buffer: unused slots must be zero (they sort last)
     if (!limited) cudaMemsetAsync(ws.accepted, 0, sizeof(unsigned long long) * (size_t)ws.cap, s);
     if (min_distance >= 1.0) {
-        cudaMemsetAsync(ws.round_counters, 0, sizeof(int) * 2 * kMaxGreedyRounds, s);
         if (limited) {
             // pass 1: the strongest ~4*max_corners candidates
-            cudaMemsetAsync(ws.sel, 0, sizeof(int) * 8, s);
             compact_strong_kernel<<<sm_count * 4, 256, 0, s>>>(cand, cand_count, cand_cap, ws.hist, 4 * max_corners,
                                                                ws.strong, ws.sel + 1);
             launch_greedy(ws.strong, ws.sel + 1, cand_cap, eig, eig_pitch, state, state_pitch, w, h, min_distance, ws,
@@ -436,9 +446,11 @@ void launch_select(const unsigned long long* cand, const int* cand_count, int ca
     }
     // keys: [63:32] ordered value, [31:0] address (< w*h); zero keys sort last
     if (limited) {
-        rank_threshold_kernel<<<1, RANK_THREADS, 0, s>>>(ws.accepted_count, ws.kept_hist, max_corners, kps_cap, ws.sel);
+        // the short list lives in the (otherwise unused on this path) sort output buffer
+        compact_top_kernel<<<sm_count, 256, 0, s>>>(ws.accepted, ws.accepted_count, ws.kept_hist, max_corners, kps_cap,
+                                                    ws.sorted, ws.sel, kps_count);
         select_rank_emit_kernel<<<sm_count, RANK_THREADS, RANK_SMEM_KEYS * sizeof(unsigned long long), s>>>(
-            ws.accepted, ws.accepted_count, ws.sel, max_corners, w, kps_out, kps_cap, kps_count);
+            ws.sorted, ws.sel, kps_count, w, kps_out);
     } else {
         size_t temp = ws.cub_temp_bytes;
         cub::DeviceRadixSort::SortKeysDescending(ws.cub_temp, temp, ws.accepted, ws.sorted, ws.cap, 0, 64, s);
