@@ -172,7 +172,7 @@ static int run_detector(pc_ctx* c, FrameSlot* f, const pc_gftt_opts* go, cudaStr
     span_end(c, s);
     f->has_kps = true;
     f->n_kps_host = -1;
-    return check_launch(c, "detector", go->max_corners > 0 ? 8 : 6);
+    return check_launch(c, "detector", 6);
 }
 
 static LKParams make_lk_params(const pc_flow_opts* fo) {
@@ -274,7 +274,7 @@ pc_ctx::~pc_ctx() {
         cudaFree(s.kps); cudaFree(s.n_kps);
     }
     cudaFree(eig); cudaFree(state); cudaFree(cell_max); cudaFree(cand); cudaFree(det_zero);
-    cudaFree(sel.accepted); cudaFree(sel.sorted); cudaFree(sel.cub_temp); cudaFree(sel.strong);
+    cudaFree(sel.accepted); cudaFree(sel.sorted); cudaFree(sel.cub_temp); cudaFree(sel.strong); cudaFree(sel.bin_start);
     cudaFree(lk_next); cudaFree(lk_status); cudaFree(lk_err);
     free_pair_out(sync_out, false);
     cudaFree(rgb_scratch);
@@ -418,8 +418,8 @@ int pc_create(const pc_limits* limits, pc_ctx** out) {
     PC_CUDA(nullptr, cudaMalloc(&cp->cand, sizeof(unsigned long long) * cp->cand_cap));
     // one block holds every detector counter that must be zero at the start of a frame, so the init
     // launch of the min-eig stage clears them all: [0] candidate count, [8..15] select scratch,
-    // then the greedy round counters and the two 4096-bin value histograms
-    cp->det_zero_ints = 16 + 2 * kMaxGreedyRounds + 2 * 4096;
+    // then the greedy round counters, the two 4096-bin value histograms and the short list's bin cursors
+    cp->det_zero_ints = 16 + 2 * kMaxGreedyRounds + 3 * 4096;
     PC_CUDA(nullptr, cudaMalloc(&cp->det_zero, sizeof(int) * cp->det_zero_ints));
     PC_CUDA(nullptr, cudaMemset(cp->det_zero, 0, sizeof(int) * cp->det_zero_ints));
     cp->cand_count = cp->det_zero;
@@ -432,6 +432,8 @@ int pc_create(const pc_limits* limits, pc_ctx** out) {
     cp->sel.round_counters = cp->det_zero + 16;
     cp->sel.hist = cp->sel.round_counters + 2 * kMaxGreedyRounds;
     cp->sel.kept_hist = cp->sel.hist + 4096;
+    cp->sel.bin_cursor = cp->sel.kept_hist + 4096;
+    PC_CUDA(nullptr, cudaMalloc(&cp->sel.bin_start, sizeof(int) * 4096));
     PC_CUDA(nullptr, cudaMalloc(&cp->sel.strong, sizeof(unsigned long long) * cp->cand_cap));
     cp->sel.cub_temp_bytes = select_cub_temp_bytes(cp->cand_cap);
     PC_CUDA(nullptr, cudaMalloc(&cp->sel.cub_temp, cp->sel.cub_temp_bytes));

@@ -143,45 +143,33 @@ struct PadPlanes {
 };
 
 // Work items of a plane: the top and bottom bands as aligned 4-byte words (corners included), then
-// the left and right bands as one 16-byte run per row and side.  data is 16-byte aligned and the
-// pitch a multiple of 128, so every store is a full aligned word.
+// the left and right bands one byte per thread (16 consecutive lanes cover one row's run, so a warp
+// touches two rows instead of 32).  Both parts read only interior pixels, so they do not depend on
+// each other's writes.
 __global__ void __launch_bounds__(256) pad_border_kernel(PadPlanes P) {
     const int L = blockIdx.y;
     const int w = P.w[L], h = P.h[L], pitch = P.pitch[L];
     uint8_t* img = P.data[L];
     const int words = (w + 2 * kPadX + 3) / 4;             // per band row, from x = -kPadX
     const int n_rows = 2 * kPadY * words;
-    const int n_cols = 2 * h;
+    const int n_cols = 2 * kPadX * h;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_rows + n_cols; i += gridDim.x * blockDim.x) {
-        if (i < n_rows) {
-            const int r = i / words;
-            const int x0 = (i - r * words) * 4 - kPadX;
+        if (i < n_cols) {
+            const int y = i / (2 * kPadX);
+            const int c = i - y * (2 * kPadX);
+            const int x = c < kPadX ? c - kPadX : w + (c - kPadX);
+            uint8_t* row = img + (ptrdiff_t)y * pitch;
+            row[x] = row[reflect101(x, w)];
+        } else {
+            const int j = i - n_cols;
+            const int r = j / words;
+            const int x0 = (j - r * words) * 4 - kPadX;
             const int y = r < kPadY ? r - kPadY : h + (r - kPadY);
             const uint8_t* src = img + (ptrdiff_t)reflect101(y, h) * pitch;
             uint32_t v = 0;
 #pragma unroll
             for (int k = 0; k < 4; k++) v |= (uint32_t)src[reflect101(x0 + k, w)] << (8 * k);
             *reinterpret_cast<uint32_t*>(img + (ptrdiff_t)y * pitch + x0) = v;
-        } else {
-            const int j = i - n_rows;
-            const int y = j >> 1;
-            uint8_t* row = img + (ptrdiff_t)y * pitch;
-            if (j & 1) {                                    // right band: x = w .. w+15 (bytes, w need not be aligned)
-                uint8_t v[kPadX];                           // all loads first: the stores may alias them for the compiler
-#pragma unroll
-                for (int k = 0; k < kPadX; k++) v[k] = row[reflect101(w + k, w)];
-#pragma unroll
-                for (int k = 0; k < kPadX; k++) row[w + k] = v[k];
-            } else {                                        // left band: x = -16 .. -1
-                uint32_t q[4];
-#pragma unroll
-                for (int g = 0; g < 4; g++) {
-                    q[g] = 0;
-#pragma unroll
-                    for (int k = 0; k < 4; k++) q[g] |= (uint32_t)row[reflect101(-kPadX + 4 * g + k, w)] << (8 * k);
-                }
-                *reinterpret_cast<uint4*>(row - kPadX) = make_uint4(q[0], q[1], q[2], q[3]);
-            }
         }
     }
 }
@@ -191,9 +179,9 @@ void launch_pad_border(const Image8* planes, int levels, cudaStream_t s) {
     int most = 0;
     for (int L = 0; L < levels; L++) {
         P.data[L] = planes[L].data; P.w[L] = planes[L].w; P.h[L] = planes[L].h; P.pitch[L] = planes[L].pitch;
-        most = std::max(most, 2 * kPadY * ((planes[L].w + 2 * kPadX + 3) / 4) + 2 * planes[L].h);
+        most = std::max(most, 2 * kPadY * ((planes[L].w + 2 * kPadX + 3) / 4) + 2 * kPadX * planes[L].h);
     }
-    dim3 grid(std::min((most + 255) / 256, 296), levels);
+    dim3 grid(std::min((most + 255) / 256, 592), levels);
     pad_border_kernel<<<grid, 256, 0, s>>>(P);
 }
 

@@ -61,7 +61,9 @@ struct SelectWorkspace {
     int* remaining;                    // device int: undecided candidates left (0 = converged)
     int* hist;                         // 4096 ints: 12-bit value histogram of all candidates (written by K5)
     int* kept_hist;                    // 4096 ints: 12-bit value histogram of kept keys
-    int* sel;                          // 8 ints: [1] strong count, [2] threshold bin, [3] short-list size, [4] its fill cursor
+    int* sel;                          // 8 ints: [1] strong count, [2] threshold bin, [3] short-list size
+    int* bin_cursor;                   // 4096 ints, zero on entry: fill cursors of the short list's bin groups
+    int* bin_start;                    // 4096 ints: first slot of each bin group in the short list
     void* cub_temp; size_t cub_temp_bytes;
     int cap;
     int sorted_cap;

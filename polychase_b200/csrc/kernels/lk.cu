@@ -294,9 +294,16 @@ __global__ void __launch_bounds__(1024) lk_compact_kernel(LKBatch batch) {
     for (int start = 0; start < n; start += 1024 * CP_PER, buf ^= 1) {
         const int i0 = start + threadIdx.x * CP_PER;
         unsigned keep = 0;
+        if (i0 + CP_PER <= n && (reinterpret_cast<uintptr_t>(pr.status) & 7) == 0) {
+            const uint2 sv = __ldg(reinterpret_cast<const uint2*>(pr.status + i0));
 #pragma unroll
-        for (int k = 0; k < CP_PER; k++)
-            if (i0 + k < n && pr.status[i0 + k] == 1) keep |= 1u << k;
+            for (int k = 0; k < CP_PER; k++)
+                if ((((k < 4 ? sv.x : sv.y) >> (8 * (k & 3))) & 0xffu) == 1u) keep |= 1u << k;
+        } else {
+#pragma unroll
+            for (int k = 0; k < CP_PER; k++)
+                if (i0 + k < n && pr.status[i0 + k] == 1) keep |= 1u << k;
+        }
         const int mine = __popc(keep);
         int incl = mine;
 #pragma unroll
@@ -316,14 +323,25 @@ __global__ void __launch_bounds__(1024) lk_compact_kernel(LKBatch batch) {
         const int before = __shfl_sync(0xffffffffu, wincl - wt, wid);
         const int total = __shfl_sync(0xffffffffu, wincl, 31);
         int slot = base + before + incl - mine;
+        // every load before the first store: the outputs may alias the inputs as far as the compiler
+        // knows, and a load -> store -> load chain costs one L2 round trip per row
+        float2 t[CP_PER];
+        float e[CP_PER];
+#pragma unroll
+        for (int k = 0; k < CP_PER; k++) {
+            t[k] = make_float2(0.f, 0.f);
+            e[k] = 0.f;
+            if (keep & (1u << k)) {
+                t[k] = __ldg(reinterpret_cast<const float2*>(pr.next + 2 * (i0 + k)));
+                e[k] = __ldg(pr.err + i0 + k);
+            }
+        }
 #pragma unroll
         for (int k = 0; k < CP_PER; k++) {
             if (keep & (1u << k)) {
-                const int i = i0 + k;
-                const float2 t = *reinterpret_cast<const float2*>(pr.next + 2 * i);
-                pr.out_idx[slot] = (uint32_t)i;
-                *reinterpret_cast<float2*>(pr.out_tgt + 2 * slot) = t;
-                pr.out_err[slot] = pr.err[i];
+                pr.out_idx[slot] = (uint32_t)(i0 + k);
+                *reinterpret_cast<float2*>(pr.out_tgt + 2 * slot) = t[k];
+                pr.out_err[slot] = e[k];
                 slot++;
             }
         }

@@ -25,8 +25,6 @@
 //     warp takes only when one of its keypoints' patches leaves the image at that level.
 // Integer stages are exact and float stages use explicit-rounding intrinsics (file is compiled
 // with -fmad=false), so results are bit-identical to the oracle (tests/test_gpu_analyze.py).
-#include <cstdlib>
-
 #include "common.cuh"
 #include "kernels.h"
 
@@ -100,7 +98,7 @@ __device__ __forceinline__ void template_pass(const LevelRef& A, int ipx, int ip
                                                    int w01, int w10, int w11, int (&Ival)[20], int (&Ix)[20],
                                                    int (&Iy)[20], float& a11, float& a12, float& a22) {
     const int X0 = ipx + xa - 1;                      // first byte of column set 0 (taps X-1 .. X+2)
-    const uint8_t* rowp = A.img + (size_t)(ipy - 1) * A.pitch + (X0 & ~3);
+    int off = (ipy - 1) * A.pitch + (X0 & ~3);      // 32-bit row offsets: one wide add per row address
     const int step = (X0 & 3) * 8;
     const int step2 = simd ? 0 : 8;                   // tail: set 1 starts one byte after set 0
     const uint32_t wa = pack_weights(w00, w01), wb = pack_weights(w10, w11);
@@ -118,8 +116,8 @@ __device__ __forceinline__ void template_pass(const LevelRef& A, int ipx, int ip
 #pragma unroll
     for (int rr = 0; rr < WIN + 3; rr++) {            // source rows ipy-1 .. ipy+11
         uint32_t w0, w1, w2;
-        load_row_words(rowp, w0, w1, w2);
-        rowp += A.pitch;
+        load_row_words(A.img + (ptrdiff_t)off, w0, w1, w2);
+        off += A.pitch;
         uint32_t Q[2];
         Q[0] = __funnelshift_r(w0, w1, step);         // bytes g0 g1 g2 g3 of set 0
         const uint32_t N = __funnelshift_r(w1, w2, step);
@@ -191,7 +189,7 @@ __device__ __forceinline__ void window_pass(const LevelRef& B, int inx, int iny,
                                                  const int (&Ix)[20], const int (&Iy)[20], float& bx, float& by,
                                                  int& esum) {
     const int X0 = inx + xa;
-    const uint8_t* rowp = B.img + (size_t)iny * B.pitch + (X0 & ~3);
+    int off = iny * B.pitch + (X0 & ~3);           // 32-bit row offsets: one IMAD.WIDE per row address
     const int step = (X0 & 3) * 8;
     const int step2 = simd ? step : 8;
     const uint32_t wa = pack_weights(w00, w01), wb = pack_weights(w10, w11);
@@ -200,8 +198,8 @@ __device__ __forceinline__ void window_pass(const LevelRef& B, int inx, int iny,
 #pragma unroll
     for (int rr = 0; rr <= WIN; rr++) {               // target rows iny .. iny+10
         uint32_t w0, w1, w2;
-        load_row_words(rowp, w0, w1, w2);
-        rowp += B.pitch;
+        load_row_words(B.img + (ptrdiff_t)off, w0, w1, w2);
+        off += B.pitch;
         uint32_t P[2];
         P[0] = __funnelshift_r(w0, w1, step);         // bytes X0, X0+1 in the low half (dp2a.lo)
         P[1] = __funnelshift_r(simd ? w1 : P[0], w2, step2);
@@ -368,27 +366,10 @@ __global__ void __launch_bounds__(LK_WARPS * 32, 4) lk10_kernel(LKBatch batch, L
 
 }  // namespace
 
-// The kernel needs the whole register file at 4 blocks per SM.  PC_LK_BLOCKS_PER_SM = 1..3 caps its
-// residency (through an unused dynamic shared memory reservation) so that the kernels of the next
-// frame's detector, queued on another stream, find room next to it.
-static int lk10_smem_reservation() {
-    static int bytes = -1;
-    if (bytes < 0) {
-        bytes = 0;
-        const char* e = getenv("PC_LK_BLOCKS_PER_SM");
-        const int n = e ? atoi(e) : 0;
-        if (n >= 1 && n <= 3) {
-            bytes = (200 * 1024 / n) & ~1023;
-            cudaFuncSetAttribute(lk10_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-        }
-    }
-    return bytes;
-}
-
 void launch_lk10(const LKBatch& batch, const LKParams& p, cudaStream_t s) {
     const int per_block = LK_WARPS * PTS_PER_WARP;
     dim3 grid((batch.cap + per_block - 1) / per_block, batch.num_pairs);
-    lk10_kernel<<<grid, LK_WARPS * 32, lk10_smem_reservation(), s>>>(batch, p);
+    lk10_kernel<<<grid, LK_WARPS * 32, 0, s>>>(batch, p);
 }
 
 }  // namespace pc

@@ -314,20 +314,31 @@ __global__ void __launch_bounds__(NMS_WARPS * 32) nms_candidates_kernel(
     };
     // thresholded values for columns xb-1 .. xb+4 (0 outside the image: never a max, and border
     // pixels are never candidates)
+    // the common case: the whole tile (with its one-pixel ring) lies in one grid cell, so one
+    // threshold serves every pixel and the per-row cell arithmetic disappears
+    const int tx_lo = max(tx * 128 - 1, 0), tx_hi = min(tx * 128 + 128, w - 1);
+    const int ty_lo = max(y0 - 1, 0), ty_hi = min(y_end, h - 1);
+    const bool one_cell = tx_lo / grid.block_w == tx_hi / grid.block_w && ty_lo / grid.block_h == ty_hi / grid.block_h;
+    const float thr_one = thr_tab[(ty_lo / grid.block_h) * grid.grid_cols + tx_lo / grid.block_w];
     auto finish = [&](int y, const RawRow& r, float (&t)[6]) {
 #pragma unroll
         for (int j = 0; j < 6; j++) t[j] = 0.f;
         if ((unsigned)y >= (unsigned)h) return;   // warp-uniform
-        const int crow = (y / grid.block_h) * grid.grid_cols;
         const float raw[4] = {r.v.x, r.v.y, r.v.z, r.v.w};
+        float th[6];
+        if (one_cell) {
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const float th = thr_tab[crow + cxj[j + 1]];
-            t[j + 1] = (live && xb + j < w && raw[j] > th) ? raw[j] : 0.f;
+            for (int j = 0; j < 6; j++) th[j] = thr_one;
+        } else {
+            const int crow = (y / grid.block_h) * grid.grid_cols;
+#pragma unroll
+            for (int j = 0; j < 6; j++) th[j] = thr_tab[crow + cxj[j]];
         }
+#pragma unroll
+        for (int j = 0; j < 4; j++) t[j + 1] = (live && xb + j < w && raw[j] > th[j + 1]) ? raw[j] : 0.f;
         float left = __shfl_up_sync(FULL, t[4], 1), right = __shfl_down_sync(FULL, t[1], 1);
-        if (lane == 0) left = (live && xb >= 1 && r.edge > thr_tab[crow + cxj[0]]) ? r.edge : 0.f;
-        if (lane == 31) right = (xb + 4 < w && r.edge > thr_tab[crow + cxj[5]]) ? r.edge : 0.f;
+        if (lane == 0) left = (live && xb >= 1 && r.edge > th[0]) ? r.edge : 0.f;
+        if (lane == 31) right = (xb + 4 < w && r.edge > th[5]) ? r.edge : 0.f;
         t[0] = left;
         t[5] = right;
     };
@@ -342,14 +353,16 @@ __global__ void __launch_bounds__(NMS_WARPS * 32) nms_candidates_kernel(
         finish(y + 1, cur, c);
         uint32_t bits = 0;
         bool is_c[4];
+        float colmax[6];                           // max over the three rows, per column (centre included:
+#pragma unroll                                     //  v >= max(all nine) <=> v >= max(the other eight))
+        for (int j = 0; j < 6; j++) colmax[j] = fmaxf(fmaxf(a[j], b[j]), c[j]);
+        const bool row_in = y >= 1 && y < h - 1;
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             const float vmid = b[j + 1];
-            float m = fmaxf(fmaxf(a[j], a[j + 1]), a[j + 2]);
-            m = fmaxf(m, fmaxf(b[j], b[j + 2]));
-            m = fmaxf(m, fmaxf(fmaxf(c[j], c[j + 1]), c[j + 2]));
+            const float m = fmaxf(fmaxf(colmax[j], colmax[j + 1]), colmax[j + 2]);
             const int x = xb + j;
-            is_c[j] = vmid != 0.f && vmid >= m && x >= 1 && x < w - 1 && y >= 1 && y < h - 1;
+            is_c[j] = vmid != 0.f && vmid >= m && x >= 1 && x < w - 1 && row_in;
             bits |= is_c[j] ? (1u << (8 * j)) : 0u;
         }
         if (live) {

@@ -23,6 +23,7 @@
 // bin); select_rank_emit_kernel stages that short list in shared memory and ranks it by counting
 // ((value, address) descending): rank r < max_corners is keypoint r.
 // With max_corners == 0 every kept key is sorted (CUB radix sort).
+#include <algorithm>
 #include <cooperative_groups.h>
 #include <cub/device/device_radix_sort.cuh>
 
@@ -112,84 +113,6 @@ __device__ __forceinline__ int decide(unsigned long long key, int x, int y, cons
     return blocked ? 0 : ST_KEPT;
 }
 
-// list/count: candidates to decide in this launch.  If enough_at > 0 and that many corners are
-// already kept, the launch is a no-op (second, full pass of the max_corners path).
-__global__ void __launch_bounds__(256) greedy_suppress_kernel(
-    const unsigned long long* __restrict__ cand, const int* __restrict__ cand_count, int cand_cap,
-    const float* __restrict__ eig, int eig_pitch, uint8_t* state, int state_pitch, int w, int h, int R,
-    double md2, unsigned long long* __restrict__ accepted, int* accepted_count, int* kept_hist, int* round_counters,
-    int* remaining, int enough_at) {
-    cg::grid_group grid = cg::this_grid();
-    __shared__ int block_undecided;
-    if (enough_at > 0) {        // every block must take the same decision: read, barrier, then decide
-        const int kept = *((volatile int*)accepted_count);
-        grid.sync();
-        if (kept >= enough_at) return;
-    }
-    const int n = min(*cand_count, cand_cap);
-    const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
-    const int gstride = gridDim.x * blockDim.x;
-    int last = 0;
-    for (int round = 0; round < kMaxGreedyRounds; round++) {
-        if (threadIdx.x == 0) block_undecided = 0;
-        __syncthreads();
-        int undecided = 0;
-        for (int i = gtid; i < n; i += gstride) {
-            const unsigned long long key = cand[i];
-            const int addr = (int)(key & 0xffffffffu);
-            const int y = addr / w, x = addr - y * w;
-            uint8_t* sp = state + (size_t)y * state_pitch + x;
-            if (__ldcg(sp) != ST_UNDECIDED) continue;
-            int blockers[kMaxBlockers], nb;
-            int d = decide(key, x, y, eig, eig_pitch, state, state_pitch, w, h, R, md2, blockers, nb);
-            if (d == 0 && nb <= kMaxBlockers) {
-                // The blockers are stronger candidates that other (co-resident) threads are deciding
-                // right now: watch just those few state bytes for a bounded time instead of paying
-                // a grid barrier + rescan per dependency level.  States only move UNDECIDED -> final,
-                // so "a blocker got KEPT" / "all blockers got REJECTED" are final answers too.
-                for (int spin = 0; spin < kGreedySpins && d == 0; spin++) {
-                    __nanosleep(200);
-                    bool pending = false;
-                    for (int k = 0; k < nb; k++) {
-                        const uint8_t ns = __ldcg(state + blockers[k]);
-                        if (ns == ST_KEPT) d = ST_REJECTED;
-                        else if (ns == ST_UNDECIDED) pending = true;
-                    }
-                    if (d == 0 && !pending) d = ST_KEPT;
-                }
-            }
-            if (d == ST_REJECTED) {
-                *(volatile uint8_t*)sp = ST_REJECTED;
-            } else if (d == ST_KEPT) {
-                *(volatile uint8_t*)sp = ST_KEPT;
-                accepted[atomicAdd(accepted_count, 1)] = key;
-                if (kept_hist) atomicAdd(&kept_hist[(unsigned)(key >> 52)], 1);
-            } else {
-                undecided++;
-            }
-        }
-        if (undecided) atomicAdd(&block_undecided, undecided);
-        __syncthreads();
-        if (threadIdx.x == 0 && block_undecided) atomicAdd(&round_counters[round], block_undecided);
-        grid.sync();
-        last = *((volatile int*)&round_counters[round]);
-        if (last == 0) break;
-    }
-    if (gtid == 0) *remaining = last;
-}
-
-__global__ void accept_all_kernel(const unsigned long long* __restrict__ cand, const int* __restrict__ cand_count,
-                                  int cand_cap, unsigned long long* __restrict__ accepted, int* accepted_count,
-                                  int* kept_hist, int* remaining) {
-    const int n = min(*cand_count, cand_cap);
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const unsigned long long key = cand[i];
-        accepted[i] = key;
-        if (kept_hist) atomicAdd(&kept_hist[(unsigned)(key >> 52)], 1);
-    }
-    if (blockIdx.x == 0 && threadIdx.x == 0) { *accepted_count = n; *remaining = 0; }
-}
-
 // Block-wide "largest bin b whose suffix count reaches `want`" over a histogram in global memory,
 // PER_THREAD consecutive bins per thread (descending search; PER_THREAD <= 64).  Returns the bin
 // (0 if the whole histogram holds fewer than `want`) and, through *count_out, the number of
@@ -246,125 +169,228 @@ __device__ __forceinline__ int suffix_threshold_bin(const int* hist, int want, i
     return s_res[3];
 }
 
-// Strong candidates: those whose 12-bit value bin is at or above the bin at which the suffix
-// count of the NMS histogram reaches `want` (every block recomputes that bin: 4096 ints).
-__global__ void __launch_bounds__(256) compact_strong_kernel(const unsigned long long* __restrict__ cand,
-                                                             const int* __restrict__ cand_count, int cand_cap,
-                                                             const int* hist, int want,
-                                                             unsigned long long* __restrict__ strong,
-                                                             int* __restrict__ strong_count) {
-    __shared__ int s_warp[8], s_res[8];
-    int strong_total;
-    const unsigned thr = (unsigned)suffix_threshold_bin<256, 16>(hist, want, s_warp, s_res, &strong_total);
-    const int n = min(*cand_count, cand_cap);
-    for (int base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
-        const int i = base + threadIdx.x;
-        unsigned long long key = 0;
-        bool keep = false;
-        if (i < n) {
-            key = cand[i];
-            keep = (unsigned)(key >> 52) >= thr;
+// One fixed-point run over list[0..n): returns the number of candidates still undecided (0 =
+// converged).  Every block of the grid must call it (grid barrier per round).
+__device__ __forceinline__ int greedy_rounds(cg::grid_group& grid, int* block_undecided,
+                                             const unsigned long long* __restrict__ list, int n,
+                                             const float* __restrict__ eig, int eig_pitch, uint8_t* state,
+                                             int state_pitch, int w, int h, int R, double md2,
+                                             unsigned long long* __restrict__ accepted, int* accepted_count,
+                                             int* kept_hist, int* round_counters) {
+    const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int gstride = gridDim.x * blockDim.x;
+    int last = 0;
+    for (int round = 0; round < kMaxGreedyRounds; round++) {
+        if (threadIdx.x == 0) *block_undecided = 0;
+        __syncthreads();
+        int undecided = 0;
+        for (int i = gtid; i < n; i += gstride) {
+            const unsigned long long key = list[i];
+            const int addr = (int)(key & 0xffffffffu);
+            const int y = addr / w, x = addr - y * w;
+            uint8_t* sp = state + (size_t)y * state_pitch + x;
+            if (__ldcg(sp) != ST_UNDECIDED) continue;
+            int blockers[kMaxBlockers], nb;
+            int d = decide(key, x, y, eig, eig_pitch, state, state_pitch, w, h, R, md2, blockers, nb);
+            if (d == 0 && nb <= kMaxBlockers) {
+                // The blockers are stronger candidates that other (co-resident) threads are deciding
+                // right now: watch just those few state bytes for a bounded time instead of paying
+                // a grid barrier + rescan per dependency level.  States only move UNDECIDED -> final,
+                // so "a blocker got KEPT" / "all blockers got REJECTED" are final answers too.
+                for (int spin = 0; spin < kGreedySpins && d == 0; spin++) {
+                    __nanosleep(100);
+                    bool pending = false;
+                    for (int k = 0; k < nb; k++) {
+                        const uint8_t ns = __ldcg(state + blockers[k]);
+                        if (ns == ST_KEPT) d = ST_REJECTED;
+                        else if (ns == ST_UNDECIDED) pending = true;
+                    }
+                    if (d == 0 && !pending) d = ST_KEPT;
+                }
+            }
+            if (d == ST_REJECTED) {
+                *(volatile uint8_t*)sp = ST_REJECTED;
+            } else if (d == ST_KEPT) {
+                *(volatile uint8_t*)sp = ST_KEPT;
+                accepted[atomicAdd(accepted_count, 1)] = key;
+                if (kept_hist) atomicAdd(&kept_hist[(unsigned)(key >> 52)], 1);
+            } else {
+                undecided++;
+            }
         }
-        const unsigned m = __ballot_sync(0xffffffffu, keep);
-        if (m) {
-            const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
-            int b = 0;
-            if (lane == leader) b = atomicAdd(strong_count, __popc(m));
-            b = __shfl_sync(0xffffffffu, b, leader);
-            if (keep) strong[b + __popc(m & ((1u << lane) - 1))] = key;
-        }
+        if (undecided) atomicAdd(block_undecided, undecided);
+        __syncthreads();
+        if (threadIdx.x == 0 && *block_undecided) atomicAdd(&round_counters[round], *block_undecided);
+        grid.sync();
+        last = *((volatile int*)&round_counters[round]);
+        if (last == 0) break;
     }
+    return last;
+}
+
+// The whole suppression stage in one cooperative launch.
+//   strong_want == 0 (max_corners == 0): one fixed-point run over every candidate.
+//   strong_want  > 0: (1) the candidates at or above the value bin at which the suffix count of the
+//   NMS histogram reaches strong_want are appended to `strong` (every block recomputes that bin:
+//   4096 ints); (2) fixed point over `strong`; (3) only if that kept fewer than max_corners corners,
+//   a second run over everything (decided candidates are skipped through the state map).
+__global__ void __launch_bounds__(256) greedy_suppress_kernel(
+    const unsigned long long* __restrict__ cand, const int* __restrict__ cand_count, int cand_cap,
+    const float* __restrict__ eig, int eig_pitch, uint8_t* state, int state_pitch, int w, int h, int R,
+    double md2, unsigned long long* __restrict__ accepted, int* accepted_count, int* kept_hist, int* round_counters,
+    int* remaining, const int* value_hist, int strong_want, unsigned long long* __restrict__ strong,
+    int* strong_count, int max_corners) {
+    cg::grid_group grid = cg::this_grid();
+    __shared__ int block_undecided;
+    __shared__ int s_warp[8], s_res[8];
+    const int n = min(*cand_count, cand_cap);
+    const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
+    int last;
+    if (strong_want > 0) {
+        int strong_total;
+        const unsigned thr = (unsigned)suffix_threshold_bin<256, 16>(value_hist, strong_want, s_warp, s_res, &strong_total);
+        for (int base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
+            const int i = base + threadIdx.x;
+            unsigned long long key = 0;
+            bool keep = false;
+            if (i < n) {
+                key = cand[i];
+                keep = (unsigned)(key >> 52) >= thr;
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, keep);
+            if (m) {
+                const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+                int b = 0;
+                if (lane == leader) b = atomicAdd(strong_count, __popc(m));
+                b = __shfl_sync(0xffffffffu, b, leader);
+                if (keep) strong[b + __popc(m & ((1u << lane) - 1))] = key;
+            }
+        }
+        grid.sync();
+        const int n1 = min(*((volatile int*)strong_count), cand_cap);
+        last = greedy_rounds(grid, &block_undecided, strong, n1, eig, eig_pitch, state, state_pitch, w, h, R, md2,
+                             accepted, accepted_count, kept_hist, round_counters);
+        // every block is past the barrier of the last round: the kept count is final and uniform
+        if (*((volatile int*)accepted_count) < max_corners)
+            last = greedy_rounds(grid, &block_undecided, cand, n, eig, eig_pitch, state, state_pitch, w, h, R, md2,
+                                 accepted, accepted_count, kept_hist, round_counters + kMaxGreedyRounds);
+    } else {
+        last = greedy_rounds(grid, &block_undecided, cand, n, eig, eig_pitch, state, state_pitch, w, h, R, md2,
+                             accepted, accepted_count, kept_hist, round_counters);
+    }
+    if (gtid == 0) *remaining = last;
+}
+
+__global__ void accept_all_kernel(const unsigned long long* __restrict__ cand, const int* __restrict__ cand_count,
+                                  int cand_cap, unsigned long long* __restrict__ accepted, int* accepted_count,
+                                  int* kept_hist, int* remaining) {
+    const int n = min(*cand_count, cand_cap);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const unsigned long long key = cand[i];
+        accepted[i] = key;
+        if (kept_hist) atomicAdd(&kept_hist[(unsigned)(key >> 52)], 1);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) { *accepted_count = n; *remaining = 0; }
 }
 
 // ---- final selection: the max_corners strongest kept keys, in order, as keypoints -------------
-// compact_top_kernel: every CTA finds the 12-bit value bin that holds the k-th strongest kept key
-// (k = min(max_corners, kept); 16 KB histogram, recomputed per CTA) and appends its share of the keys
-// at or above that bin to `top` (m >= k of them: k plus part of one bin's population).
-// select_rank_emit_kernel: every CTA stages top[0..m) in shared memory and ranks its share by
-// counting (rank = number of keys that are larger; keys are unique), one warp per key:
-// rank < k -> keypoint slot `rank`.  The m^2 comparisons spread over the grid are a few
-// microseconds, where a single-CTA sort was ~130 us.
-constexpr int RANK_THREADS = 1024;
-constexpr int RANK_SMEM_KEYS = 16384;                       // 128 KB of dynamic shared memory
+// The 12-bit value histogram of the kept keys is a counting sort's first half: the rank of a key is
+// (number of keys in higher bins) + (its rank inside its own bin).
+// compact_top_kernel: every CTA builds the exclusive suffix sums of the histogram in shared memory,
+// finds the bin `thr` that holds the k-th strongest key (k = min(max_corners, kept)) and scatters its
+// share of the keys at or above `thr` into `top`, grouped by bin (group start = suffix sum, slot inside
+// the group from a per-bin cursor).  m = keys at or above `thr` = k plus part of one bin.
+// select_rank_emit_kernel: one warp per key of top[0..m) counts the larger keys of its own group
+// (a few hundred entries): rank < k -> keypoint slot `rank`.
+constexpr int TOP_BINS = 4096;
 
-// sel[2] = threshold bin, sel[3] = m, sel[4] = fill cursor of top[] (zero on entry)
+// sel[2] = threshold bin, sel[3] = m.  bin_cursor[TOP_BINS] is zero on entry; bin_start is written by
+// CTA 0 (suffix sums of the bins >= thr).
 __global__ void __launch_bounds__(256) compact_top_kernel(const unsigned long long* __restrict__ accepted,
                                                           const int* __restrict__ accepted_count,
                                                           const int* __restrict__ kept_hist, int max_corners,
                                                           int kps_cap, unsigned long long* __restrict__ top,
-                                                          int* __restrict__ sel, int* __restrict__ kps_count) {
-    __shared__ int s_warp[8], s_res[8];
+                                                          int* __restrict__ sel, int* __restrict__ kps_count,
+                                                          int* __restrict__ bin_cursor, int* __restrict__ bin_start) {
+    __shared__ int s_suf[TOP_BINS];                          // keys in bins > b
+    __shared__ int s_warp[8];
+    __shared__ int s_thr, s_m;
+    const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
     const int n = *accepted_count;
     const int k = min(min(max_corners, n), kps_cap);
-    if (blockIdx.x == 0 && threadIdx.x == 0) *kps_count = k;
+    if (blockIdx.x == 0 && t == 0) *kps_count = k;
     if (k == 0) {
-        if (blockIdx.x == 0 && threadIdx.x == 0) { sel[2] = 0; sel[3] = 0; }
+        if (blockIdx.x == 0 && t == 0) { sel[2] = 0; sel[3] = 0; }
         return;
     }
-    int m = 0;
-    const unsigned thr = (unsigned)suffix_threshold_bin<256, 16>(kept_hist, k, s_warp, s_res, &m);
-    if (blockIdx.x == 0 && threadIdx.x == 0) { sel[2] = (int)thr; sel[3] = m; }
-    const int lane = threadIdx.x & 31;
-    for (int base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
-        const int i = base + threadIdx.x;
-        unsigned long long key = 0ull;
-        bool keep = false;
-        if (i < n) {
-            key = accepted[i];
-            keep = (unsigned)(key >> 52) >= thr;
+    // thread t owns bins [16 t, 16 t + 16)
+    int hv[16];
+    {
+        const int4* hp = reinterpret_cast<const int4*>(kept_hist) + t * 4;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int4 v = __ldcg(hp + q);
+            hv[4 * q] = v.x; hv[4 * q + 1] = v.y; hv[4 * q + 2] = v.z; hv[4 * q + 3] = v.w;
         }
-        const unsigned bal = __ballot_sync(0xffffffffu, keep);
-        if (bal) {
-            const int leader = __ffs(bal) - 1;
-            int b = 0;
-            if (lane == leader) b = atomicAdd(&sel[4], __popc(bal));
-            b = __shfl_sync(0xffffffffu, b, leader);
-            if (keep) top[b + __popc(bal & ((1u << lane) - 1))] = key;
-        }
+    }
+    int own = 0;
+#pragma unroll
+    for (int q = 0; q < 16; q++) own += hv[q];
+    int v = own;                                             // suffix sum inside the warp (lanes >= lane)
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int nb = __shfl_down_sync(0xffffffffu, v, o);
+        if (lane + o < 32) v += nb;
+    }
+    if (lane == 0) s_warp[wid] = v;
+    if (t == 0) { s_thr = 0; s_m = 0; }
+    __syncthreads();
+    int above = 0;
+    for (int q = wid + 1; q < 8; q++) above += s_warp[q];
+    int run = v + above - own;                               // keys in bins above this thread's bins
+    if (t == 0) s_m = v + above;                             // whole histogram (taken when it holds < k: cannot happen, k <= n)
+    __syncthreads();
+#pragma unroll
+    for (int q = 15; q >= 0; q--) {
+        s_suf[16 * t + q] = run;
+        if (run < k && k <= run + hv[q]) { s_thr = 16 * t + q; s_m = run + hv[q]; }
+        run += hv[q];
+    }
+    __syncthreads();
+    const unsigned thr = (unsigned)s_thr;
+    if (blockIdx.x == 0) {
+        if (t == 0) { sel[2] = s_thr; sel[3] = s_m; }
+#pragma unroll
+        for (int q = 0; q < 16; q++) bin_start[16 * t + q] = s_suf[16 * t + q];
+    }
+    for (int i = blockIdx.x * blockDim.x + t; i < n; i += gridDim.x * blockDim.x) {
+        const unsigned long long key = accepted[i];
+        const unsigned bin = (unsigned)(key >> 52);
+        if (bin >= thr) top[s_suf[bin] + atomicAdd(&bin_cursor[bin], 1)] = key;
     }
 }
 
-__global__ void __launch_bounds__(RANK_THREADS) select_rank_emit_kernel(
-    const unsigned long long* __restrict__ top, const int* __restrict__ sel, const int* __restrict__ kps_count, int w,
-    float* __restrict__ kps) {
-    extern __shared__ __align__(16) unsigned long long s_keys[];
-    const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+__global__ void __launch_bounds__(256) select_rank_emit_kernel(
+    const unsigned long long* __restrict__ top, const int* __restrict__ sel, const int* __restrict__ kps_count,
+    const int* __restrict__ kept_hist, const int* __restrict__ bin_start, int w, float* __restrict__ kps) {
+    const int lane = threadIdx.x & 31;
     const int k = *kps_count;
     const int m = sel[3];
-    if (k == 0 || m == 0) return;
-    const bool in_smem = m < RANK_SMEM_KEYS;
-    if (in_smem) {
-        const ulonglong2* g2 = reinterpret_cast<const ulonglong2*>(top);
-        ulonglong2* s2 = reinterpret_cast<ulonglong2*>(s_keys);
-        for (int j = t; 2 * j + 1 < m; j += RANK_THREADS) s2[j] = g2[j];
-        if (t == 0) {
-            if (m & 1) s_keys[m - 1] = top[m - 1];
-            s_keys[m] = 0ull;                                // pad to an even count for the 16-byte loads
-        }
-        __syncthreads();
-    }
-    // this CTA's share of the list; one warp per key
-    const int per_cta = (m + gridDim.x - 1) / gridDim.x;
-    const int lo = blockIdx.x * per_cta, hi = min(lo + per_cta, m);
-    for (int i = lo + wid; i < hi; i += RANK_THREADS / 32) {
-        const unsigned long long key = in_smem ? s_keys[i] : top[i];
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < m; i += warps) {
+        const unsigned long long key = top[i];
+        const unsigned bin = (unsigned)(key >> 52);
+        const int g0 = __ldg(bin_start + bin), g1 = g0 + __ldg(kept_hist + bin);
         int cnt = 0;
-        if (in_smem) {
-            const ulonglong2* s2 = reinterpret_cast<const ulonglong2*>(s_keys);
-            for (int j = lane; 2 * j < m; j += 32) {
-                const ulonglong2 q = s2[j];
-                cnt += (q.x > key ? 1 : 0) + (q.y > key ? 1 : 0);
-            }
-        } else {                                             // pathological value plateau: scan the global list
-            for (int j = lane; j < m; j += 32) cnt += top[j] > key ? 1 : 0;
-        }
+        for (int j = g0 + lane; j < g1; j += 32) cnt += top[j] > key ? 1 : 0;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-        if (lane == 0 && cnt < k) {
+        const int rank = g0 + cnt;
+        if (lane == 0 && rank < k) {
             const int addr = (int)(key & 0xffffffffu);
             const int y = addr / w;
-            kps[2 * cnt] = (float)(addr - y * w);
-            kps[2 * cnt + 1] = (float)y;
+            kps[2 * rank] = (float)(addr - y * w);
+            kps[2 * rank + 1] = (float)y;
         }
     }
 }
@@ -392,21 +418,27 @@ size_t select_cub_temp_bytes(int cap) {
     return bytes;
 }
 
-static void launch_greedy(const unsigned long long* list, const int* count, int cap, const float* eig, int eig_pitch,
-                          uint8_t* state, int state_pitch, int w, int h, double min_distance,
-                          const SelectWorkspace& ws, int* kept_hist, int* round_counters, int enough_at, int sm_count,
+static void launch_greedy(const unsigned long long* cand, const int* cand_count, int cand_cap, const float* eig,
+                          int eig_pitch, uint8_t* state, int state_pitch, int w, int h, double min_distance,
+                          const SelectWorkspace& ws, int* kept_hist, int strong_want, int max_corners, int sm_count,
                           cudaStream_t s) {
     int R = (int)ceil(min_distance) - 1;
     double md2 = min_distance * min_distance;
-    int blocks_per_sm = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, greedy_suppress_kernel, 256, 0);
-    if (blocks_per_sm < 1) blocks_per_sm = 1;
-    if (blocks_per_sm > 2) blocks_per_sm = 2;
+    static int blocks_per_sm = 0;
+    if (!blocks_per_sm) {
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, greedy_suppress_kernel, 256, 0);
+        blocks_per_sm = std::min(std::max(blocks_per_sm, 1), 2);
+    }
     int nblocks = sm_count * blocks_per_sm;
-    void* args[] = {(void*)&list, (void*)&count, (void*)&cap, (void*)&eig, (void*)&eig_pitch, (void*)&state,
+    const int* value_hist = ws.hist;
+    unsigned long long* strong = ws.strong;
+    int* strong_count = ws.sel + 1;
+    int* round_counters = ws.round_counters;
+    void* args[] = {(void*)&cand, (void*)&cand_count, (void*)&cand_cap, (void*)&eig, (void*)&eig_pitch, (void*)&state,
                     (void*)&state_pitch, (void*)&w, (void*)&h, (void*)&R, (void*)&md2, (void*)&ws.accepted,
                     (void*)&ws.accepted_count, (void*)&kept_hist, (void*)&round_counters, (void*)&ws.remaining,
-                    (void*)&enough_at};
+                    (void*)&value_hist, (void*)&strong_want, (void*)&strong, (void*)&strong_count,
+                    (void*)&max_corners};
     cudaLaunchCooperativeKernel((void*)greedy_suppress_kernel, dim3(nblocks), dim3(256), args, 0, s);
 }
 
@@ -414,32 +446,16 @@ void launch_select(const unsigned long long* cand, const int* cand_count, int ca
                    int eig_pitch, uint8_t* state, int state_pitch, int w, int h, double min_distance,
                    int max_corners, SelectWorkspace ws, float* kps_out, int kps_cap, int* kps_count, int sm_count,
                    cudaStream_t s) {
-    // accepted_count, kept_hist, round_counters and sel are zero on entry (launch_min_eig clears the
-    // detector's counter block and the frame's counters)
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(select_rank_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)(RANK_SMEM_KEYS * sizeof(unsigned long long)));
-        attr_set = true;
-    }
+    // accepted_count, the histograms, round counters, cursors and sel are zero on entry (launch_min_eig
+    // clears the detector's counter block and the frame's counters)
     const bool limited = max_corners > 0;
     int* kept_hist = limited ? ws.kept_hist : nullptr;
     // the unlimited path sorts the whole accepted[] buffer: unused slots must be zero (they sort last)
     if (!limited) cudaMemsetAsync(ws.accepted, 0, sizeof(unsigned long long) * (size_t)ws.cap, s);
     if (min_distance >= 1.0) {
-        if (limited) {
-            // pass 1: the strongest ~4*max_corners candidates
-            compact_strong_kernel<<<sm_count * 4, 256, 0, s>>>(cand, cand_count, cand_cap, ws.hist, 4 * max_corners,
-                                                               ws.strong, ws.sel + 1);
-            launch_greedy(ws.strong, ws.sel + 1, cand_cap, eig, eig_pitch, state, state_pitch, w, h, min_distance, ws,
-                          kept_hist, ws.round_counters, 0, sm_count, s);
-            // pass 2 (no-op when pass 1 already kept max_corners corners): everything else
-            launch_greedy(cand, cand_count, cand_cap, eig, eig_pitch, state, state_pitch, w, h, min_distance, ws,
-                          kept_hist, ws.round_counters + kMaxGreedyRounds, max_corners, sm_count, s);
-        } else {
-            launch_greedy(cand, cand_count, cand_cap, eig, eig_pitch, state, state_pitch, w, h, min_distance, ws,
-                          kept_hist, ws.round_counters, 0, sm_count, s);
-        }
+        // limited: first the strongest ~4*max_corners candidates, everything only if that is not enough
+        launch_greedy(cand, cand_count, cand_cap, eig, eig_pitch, state, state_pitch, w, h, min_distance, ws, kept_hist,
+                      limited ? 4 * max_corners : 0, max_corners, sm_count, s);
     } else {
         accept_all_kernel<<<sm_count * 2, 256, 0, s>>>(cand, cand_count, cand_cap, ws.accepted, ws.accepted_count,
                                                        kept_hist, ws.remaining);
@@ -448,9 +464,9 @@ void launch_select(const unsigned long long* cand, const int* cand_count, int ca
     if (limited) {
         // the short list lives in the (otherwise unused on this path) sort output buffer
         compact_top_kernel<<<sm_count, 256, 0, s>>>(ws.accepted, ws.accepted_count, ws.kept_hist, max_corners, kps_cap,
-                                                    ws.sorted, ws.sel, kps_count);
-        select_rank_emit_kernel<<<sm_count, RANK_THREADS, RANK_SMEM_KEYS * sizeof(unsigned long long), s>>>(
-            ws.sorted, ws.sel, kps_count, w, kps_out);
+                                                    ws.sorted, ws.sel, kps_count, ws.bin_cursor, ws.bin_start);
+        select_rank_emit_kernel<<<sm_count * 4, 256, 0, s>>>(ws.sorted, ws.sel, kps_count, ws.kept_hist, ws.bin_start, w,
+                                                             kps_out);
     } else {
         size_t temp = ws.cub_temp_bytes;
         cub::DeviceRadixSort::SortKeysDescending(ws.cub_temp, temp, ws.accepted, ws.sorted, ws.cap, 0, 64, s);
