@@ -460,8 +460,14 @@ def main():
     dom_ms, dom_n = fam[dominant]
     avg_ms = dom_ms / max(dom_n, 1)
     achieved = per_launch.get(dominant, 0) / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0
+    traffic = None                                        # measured DRAM bytes per launch (ncu --set full), if captured
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get(dominant)
+        traffic = traffic and (traffic["bytes_per_launch"] if args.config == "4k" else None)
+    except Exception:
+        traffic = None
     line["roofline"] = {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                        "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                        "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                         "avg_launch_ms": avg_ms, "algorithmic_bytes_per_launch": per_launch.get(dominant, 0),
                         "share_of_step": dom_ms / step_ms if step_ms else None,
                         "per_kernel": {k: {"ms_total": v[0], "launch_groups": int(v[1]),

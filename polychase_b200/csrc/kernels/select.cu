@@ -35,7 +35,7 @@ namespace cg = cooperative_groups;
 namespace pc {
 
 enum : uint8_t { ST_NONE = 0, ST_UNDECIDED = 1, ST_KEPT = 2, ST_REJECTED = 3 };
-constexpr int kGreedySpins = 48;
+constexpr int kGreedySpins = 96;      // polls of a blocked candidate's blockers (~0.7 us each) before it waits for the next round
 
 __device__ __forceinline__ unsigned long long key_at(const float* __restrict__ eig, int eig_pitch, int w, int x,
                                                      int y) {
@@ -177,45 +177,59 @@ __device__ __forceinline__ int greedy_rounds(cg::grid_group& grid, int* block_un
                                              int state_pitch, int w, int h, int R, double md2,
                                              unsigned long long* __restrict__ accepted, int* accepted_count,
                                              int* kept_hist, int* round_counters) {
-    const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int gtid = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31;
     const int gstride = gridDim.x * blockDim.x;
     int last = 0;
     for (int round = 0; round < kMaxGreedyRounds; round++) {
         if (threadIdx.x == 0) *block_undecided = 0;
         __syncthreads();
         int undecided = 0;
-        for (int i = gtid; i < n; i += gstride) {
-            const unsigned long long key = list[i];
-            const int addr = (int)(key & 0xffffffffu);
-            const int y = addr / w, x = addr - y * w;
-            uint8_t* sp = state + (size_t)y * state_pitch + x;
-            if (__ldcg(sp) != ST_UNDECIDED) continue;
-            int blockers[kMaxBlockers], nb;
-            int d = decide(key, x, y, eig, eig_pitch, state, state_pitch, w, h, R, md2, blockers, nb);
-            if (d == 0 && nb <= kMaxBlockers) {
-                // The blockers are stronger candidates that other (co-resident) threads are deciding
-                // right now: watch just those few state bytes for a bounded time instead of paying
-                // a grid barrier + rescan per dependency level.  States only move UNDECIDED -> final,
-                // so "a blocker got KEPT" / "all blockers got REJECTED" are final answers too.
-                for (int spin = 0; spin < kGreedySpins && d == 0; spin++) {
-                    __nanosleep(100);
-                    bool pending = false;
-                    for (int k = 0; k < nb; k++) {
-                        const uint8_t ns = __ldcg(state + blockers[k]);
-                        if (ns == ST_KEPT) d = ST_REJECTED;
-                        else if (ns == ST_UNDECIDED) pending = true;
+        // whole warps iterate together (the append below is warp-aggregated)
+        for (int ib = gtid - lane; ib < n; ib += gstride) {
+            const int i = ib + lane;
+            unsigned long long key = 0ull;
+            int d = -1;                                      // -1: nothing to decide for this lane
+            if (i < n) {
+                key = list[i];
+                const int addr = (int)(key & 0xffffffffu);
+                const int y = addr / w, x = addr - y * w;
+                uint8_t* sp = state + (size_t)y * state_pitch + x;
+                if (__ldcg(sp) == ST_UNDECIDED) {
+                    int blockers[kMaxBlockers], nb;
+                    d = decide(key, x, y, eig, eig_pitch, state, state_pitch, w, h, R, md2, blockers, nb);
+                    if (d == 0 && nb <= kMaxBlockers) {
+                        // The blockers are stronger candidates that other (co-resident) threads are deciding
+                        // right now: watch just those few state bytes for a bounded time instead of paying
+                        // a grid barrier + rescan per dependency level.  States only move UNDECIDED -> final,
+                        // so "a blocker got KEPT" / "all blockers got REJECTED" are final answers too.
+                        for (int spin = 0; spin < kGreedySpins && d == 0; spin++) {
+                            __nanosleep(100);
+                            bool pending = false;
+                            for (int k = 0; k < nb; k++) {
+                                const uint8_t ns = __ldcg(state + blockers[k]);
+                                if (ns == ST_KEPT) d = ST_REJECTED;
+                                else if (ns == ST_UNDECIDED) pending = true;
+                            }
+                            if (d == 0 && !pending) d = ST_KEPT;
+                        }
                     }
-                    if (d == 0 && !pending) d = ST_KEPT;
+                    // publish the decision at once: other threads are polling this byte
+                    if (d == ST_REJECTED) *(volatile uint8_t*)sp = ST_REJECTED;
+                    else if (d == ST_KEPT) *(volatile uint8_t*)sp = ST_KEPT;
+                    else undecided++;
                 }
             }
-            if (d == ST_REJECTED) {
-                *(volatile uint8_t*)sp = ST_REJECTED;
-            } else if (d == ST_KEPT) {
-                *(volatile uint8_t*)sp = ST_KEPT;
-                accepted[atomicAdd(accepted_count, 1)] = key;
-                if (kept_hist) atomicAdd(&kept_hist[(unsigned)(key >> 52)], 1);
-            } else {
-                undecided++;
+            // the list append can wait for the warp to reconverge: one atomic per warp, not per corner
+            const unsigned kept = __ballot_sync(0xffffffffu, d == ST_KEPT);
+            if (kept) {
+                const int leader = __ffs(kept) - 1;
+                int b = 0;
+                if (lane == leader) b = atomicAdd(accepted_count, __popc(kept));
+                b = __shfl_sync(0xffffffffu, b, leader);
+                if (d == ST_KEPT) {
+                    accepted[b + __popc(kept & ((1u << lane) - 1))] = key;
+                    if (kept_hist) atomicAdd(&kept_hist[(unsigned)(key >> 52)], 1);
+                }
             }
         }
         if (undecided) atomicAdd(block_undecided, undecided);
@@ -249,6 +263,8 @@ __global__ void __launch_bounds__(256) greedy_suppress_kernel(
     if (strong_want > 0) {
         int strong_total;
         const unsigned thr = (unsigned)suffix_threshold_bin<256, 16>(value_hist, strong_want, s_warp, s_res, &strong_total);
+        // append with one global atomic per block and chunk: slots inside the block from the warp counts
+        const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
         for (int base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
             const int i = base + threadIdx.x;
             unsigned long long key = 0;
@@ -258,13 +274,17 @@ __global__ void __launch_bounds__(256) greedy_suppress_kernel(
                 keep = (unsigned)(key >> 52) >= thr;
             }
             const unsigned m = __ballot_sync(0xffffffffu, keep);
-            if (m) {
-                const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
-                int b = 0;
-                if (lane == leader) b = atomicAdd(strong_count, __popc(m));
-                b = __shfl_sync(0xffffffffu, b, leader);
-                if (keep) strong[b + __popc(m & ((1u << lane) - 1))] = key;
+            if (lane == 0) s_warp[wid] = __popc(m);
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                int tot = 0;
+#pragma unroll
+                for (int q = 0; q < 8; q++) { const int c = s_warp[q]; s_warp[q] = tot; tot += c; }
+                s_res[0] = tot ? atomicAdd(strong_count, tot) : 0;
             }
+            __syncthreads();
+            if (keep) strong[s_res[0] + s_warp[wid] + __popc(m & ((1u << lane) - 1))] = key;
+            __syncthreads();
         }
         grid.sync();
         const int n1 = min(*((volatile int*)strong_count), cand_cap);

@@ -1,0 +1,108 @@
+"""Parity at BASELINE.json's full size (4K, 8000 features/frame), through the C ABI.
+
+One frame pair is compared with the oracle bit for bit (the C restatement finishes a 4K pair in
+seconds); the streaming analyzer is then checked over a short 4K clip through properties that do
+not need the oracle: the pair set of GenerateOpticalFlowDatabase (opticalflow.cc:237-316), rows in
+ascending keypoint order, equality with the synchronous single-pair entry point, and run-to-run
+determinism (the detector's selection stage and the LK batches run concurrently on two streams)."""
+import numpy as np
+import pytest
+
+from oracle import restate, synth
+from oracle import gftt as ogftt
+
+pytestmark = pytest.mark.gpu
+
+W, H, N = 3840, 2160, 8000
+
+
+def _u32(a):
+    return np.ascontiguousarray(a).view(np.uint32)
+
+
+@pytest.fixture(scope="module")
+def ctx_4k():
+    from polychase_b200 import capi
+    c = capi.Context(max_width=W, max_height=H, max_features=N, pipeline_depth=4)
+    yield c
+    c.close()
+
+
+@pytest.fixture(scope="module")
+def clip_4k():
+    return synth.Clip(W, H, 12, seed=0)
+
+
+def test_4k_pair_bit_exact(ctx_4k, clip_4k):
+    from polychase_b200 import capi
+    g1, g2 = clip_4k.gray(0), clip_4k.gray(8)            # the widest skip: the slow LK case
+    ctx_4k.upload_gray(100, g1)
+    ctx_4k.upload_gray(108, g2)
+    got = ctx_4k.detect(100, capi.default_gftt(max_corners=N))
+    want = ogftt.gftt_from_eig(restate.min_eig(g1, mode=3), max_corners=N)
+    assert got.shape == (N, 2)
+    assert np.array_equal(got, want)
+    L1, L2 = restate.pyramid(g1, 3), restate.pyramid(g2, 3)
+    for L in range(4):
+        assert np.array_equal(ctx_4k.read_level(108, L), L2[L])
+    wn, ws, we = restate.lk(L1, L2, want)
+    idx, tgt, err = ctx_4k.lk_pair(100, 108)
+    ok = ws == 1
+    assert 0.9 * N < ok.sum() <= N
+    assert np.array_equal(idx, np.nonzero(ok)[0].astype(np.uint32))
+    assert np.array_equal(_u32(tgt), _u32(wn[ok]))
+    assert np.array_equal(_u32(err), _u32(we[ok]))
+
+
+def _analyze(ctx, frames, first, n):
+    from polychase_b200 import capi
+    go = capi.default_gftt(max_corners=N)
+    ctx.analyze_begin(W, H, first, n, go)
+    kps, pairs = {}, {}
+
+    def take(r):
+        kps[r["frame_id"]] = np.array(r["keypoints"]).copy()
+        for (a, b, rows, idx, tgt, err) in r["pairs"]:
+            pairs[(a, b)] = (np.array(idx).copy(), np.array(tgt).copy(), np.array(err).copy())
+
+    for k in range(first, first + n):
+        ctx.analyze_push(k, frames[k])
+        if ctx.analyze_pending() >= 4:
+            take(ctx.analyze_pop())
+    while ctx.analyze_pending():
+        take(ctx.analyze_pop())
+    ctx.analyze_end()
+    return kps, pairs
+
+
+def test_4k_streaming_properties(ctx_4k, clip_4k):
+    F = 10
+    frames = {k: clip_4k.rgb(k) for k in range(F)}
+    kps, pairs = _analyze(ctx_4k, frames, 0, F)
+    expect = sorted((a, a + d) for a in range(F) for d in (-8, -4, -2, -1, 1, 2, 4, 8) if 0 <= a + d < F)
+    assert sorted(pairs) == expect and len(expect) == 8 * F - 30
+    for k in range(F):
+        assert kps[k].shape == (N, 2)
+        assert len(np.unique(kps[k], axis=0)) == N                       # distinct corners
+        d = kps[k][:, None, :2][:64] - kps[k][None, :, :2]              # min_distance 5 (gftt.cc:100-164)
+        d2 = (d ** 2).sum(-1)
+        d2[np.arange(64), np.arange(64)] = 1e9
+        assert d2.min() >= 25.0
+    for (a, b), (idx, tgt, err) in pairs.items():
+        assert len(idx) == len(tgt) == len(err) <= N
+        assert np.all(np.diff(idx.astype(np.int64)) > 0)                 # order-preserving status filter
+        assert np.all(np.isfinite(tgt)) and np.all(err >= 0)
+        assert len(idx) > 0.9 * N
+    # the synchronous single-pair entry point gives the same rows as the batched stream
+    for (a, b) in [(9, 1), (1, 9), (8, 9), (5, 3)]:
+        idx, tgt, err = ctx_4k.lk_pair(a, b)
+        assert np.array_equal(idx, pairs[(a, b)][0])
+        assert np.array_equal(_u32(tgt), _u32(pairs[(a, b)][1]))
+        assert np.array_equal(_u32(err), _u32(pairs[(a, b)][2]))
+    # run-to-run determinism of the two-stream pipeline
+    kps2, pairs2 = _analyze(ctx_4k, frames, 0, F)
+    for k in range(F):
+        assert np.array_equal(kps[k], kps2[k])
+    for key in pairs:
+        for x, y in zip(pairs[key], pairs2[key]):
+            assert np.array_equal(_u32(x), _u32(y))
