@@ -51,7 +51,7 @@ typedef struct pc_limits {
                             runs with max_corners==0 (unlimited, gftt.h:10) results above
                             this cap are an error [16384] */
     int ring_frames;     /* frame slots kept resident (>= 9 for the +-8 window) [20] */
-    int pipeline_depth;  /* frames in flight in the streaming analyzer [4] */
+    int pipeline_depth;  /* frames in flight in the streaming analyzer [8] */
 } pc_limits;
 
 /* GFTTOptions, /root/reference/cpp/feature_detection/gftt.h:5-21 (same defaults). */

@@ -341,7 +341,7 @@ int pc_create(const pc_limits* limits, pc_ctx** out) {
     if (lim.max_height <= 0) lim.max_height = 2160;
     if (lim.max_features <= 0) lim.max_features = 16384;
     if (lim.ring_frames <= 0) lim.ring_frames = 20;
-    if (lim.pipeline_depth <= 0) lim.pipeline_depth = 4;
+    if (lim.pipeline_depth <= 0) lim.pipeline_depth = 8;
     if (lim.ring_frames < 9 + lim.pipeline_depth) lim.ring_frames = 9 + lim.pipeline_depth;
 
     int ndev = 0;

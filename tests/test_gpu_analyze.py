@@ -143,3 +143,43 @@ def test_streaming_analyzer_matches_pairwise(ctx_small):
         assert np.array_equal(idx, np.nonzero(ok)[0].astype(np.uint32))
         assert np.array_equal(_u32(tgt), _u32(wn[ok]))
         assert np.array_equal(_u32(err), _u32(we[ok]))
+
+
+@pytest.mark.parametrize("kw", [
+    dict(min_distance=1.0, max_corners=0), dict(min_distance=3.0, max_corners=700),
+    dict(min_distance=5.4, max_corners=0), dict(min_distance=7.5, max_corners=400),      # R > 4: generic disc scan
+    dict(min_distance=0.5, max_corners=0), dict(min_distance=0.5, max_corners=900),      # < 1: nothing is suppressed
+    dict(min_distance=30.0, max_corners=500),     # the strongest 4*max_corners keep too few: second pass over everything
+    dict(quality_level=0.4, max_corners=8000),    # fewer corners than max_corners
+    dict(quality_level=0.001, max_corners=1000),
+    dict(grid_rows=1, grid_cols=1, max_corners=800), dict(grid_rows=2, grid_cols=3, max_corners=0),
+    dict(grid_rows=8, grid_cols=8, max_corners=1200),
+])
+def test_detector_option_variants(ctx_small, kw):
+    """Every branch of the selection stage (gftt.cc:38-192) against the restated detector."""
+    from polychase_b200 import capi
+    w, h = 803, 601
+    g = synth.Clip(w, h, 1, seed=17).gray(0)
+    ctx_small.upload_gray(30, g)
+    got = ctx_small.detect(30, capi.default_gftt(**kw))
+    want = ogftt.detect(g, 3, **kw)
+    assert got.shape == want.shape
+    assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("w,h", [(16, 16), (17, 23), (64, 48)])
+def test_tiny_and_flat_frames(ctx_small, w, h):
+    """Smallest accepted frames, and a frame without a single corner: zero keypoints, zero flow rows."""
+    from polychase_b200 import capi
+    rng = np.random.default_rng(w + h)
+    g = rng.integers(0, 256, (h, w), dtype=np.uint8)
+    ctx_small.upload_gray(40, g)
+    got = ctx_small.detect(40, capi.default_gftt(max_corners=50))
+    want = ogftt.detect(g, 3, max_corners=50)
+    assert np.array_equal(got, want)
+    flat = np.full((h, w), 127, np.uint8)
+    ctx_small.upload_gray(41, flat)
+    assert ctx_small.detect(41, capi.default_gftt(max_corners=50)).shape == (0, 2)
+    ctx_small.upload_gray(42, g)
+    idx, tgt, err = ctx_small.lk_pair(41, 42)
+    assert len(idx) == 0 and len(tgt) == 0 and len(err) == 0
