@@ -80,8 +80,37 @@ class ClockSampler:
         self.index = index
         self.proc = None
         self.lines = []
+        self.nvml = None
+        self.samples = []          # (sm_mhz, reasons bitmask) from NVML
+        self.stop_flag = False
+
+    # NVML in-process (a sample every few milliseconds: the timed region is a fraction of a second);
+    # the nvidia-smi loop of the profiling recipe is the fallback
+    NVML_REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+
+    def _nvml_loop(self):
+        n = self.nvml
+        while not self.stop_flag:
+            try:
+                sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+                rs = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                self.samples.append((float(sm), int(rs)))
+            except Exception:
+                pass
+            time.sleep(0.004)
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+            self.thread = threading.Thread(target=self._nvml_loop, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "200",
@@ -96,6 +125,17 @@ class ClockSampler:
             self.lines.append(line.strip())
 
     def stop(self) -> dict:
+        if self.nvml is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=1)
+            sm = [x[0] for x in self.samples]
+            reasons = set()
+            for _, rs in self.samples:
+                for bit, nm in self.NVML_REASONS.items():
+                    if rs & bit:
+                        reasons.add(nm)
+            return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.sm_max,
+                    "reasons": sorted(reasons), "samples": len(sm), "source": "nvml"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -117,9 +157,10 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(nm)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi"}
 
 
+# ------------------------------------------------------------------------------------------
 def read_peak_hbm():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -198,6 +239,7 @@ def main():
               "width": w, "height": h, "max_corners": max_corners, "frames_per_step": fps,
               "parallelism": f"frames sharded x{world}" if world > 1 else "single GPU",
               "frames_in_flight": args.depth,
+              "host": "one process per GPU, bound to the GPU's CPU affinity (NVML)",
               "l2_policy": "inputs larger than L2 (each step streams fresh frames)"}
 
     if args.impl == "reference":
@@ -221,6 +263,14 @@ def main():
     from polychase_b200 import capi
 
     torch.cuda.set_device(local_rank)
+    numa = None
+    try:       # run this rank (and allocate its pinned frame ring) on the CPUs next to its GPU
+        import pynvml
+        pynvml.nvmlInit()
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local_rank))
+        numa = len(os.sched_getaffinity(0))
+    except Exception:
+        numa = None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
