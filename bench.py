@@ -263,14 +263,13 @@ def main():
     from polychase_b200 import capi
 
     torch.cuda.set_device(local_rank)
-    numa = None
+    orig_affinity = os.sched_getaffinity(0)
     try:       # run this rank (and allocate its pinned frame ring) on the CPUs next to its GPU
         import pynvml
         pynvml.nvmlInit()
         pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local_rank))
-        numa = len(os.sched_getaffinity(0))
     except Exception:
-        numa = None
+        pass
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
@@ -533,6 +532,10 @@ def main():
 
     # ---- CPU baseline on a bounded sample (rank 0, N=1 only) -----------------------------
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:                                              # the CPU arm gets every host core back
+            os.sched_setaffinity(0, orig_affinity)
+        except Exception:
+            pass
         val, dt, pairs, cores, sample = cpu_reference_run(args.config, 1, 1, args.cpu_baseline_frames, 4)
         line["cpu_baseline"] = {"value": val, "unit": "frame-pairs/s", "cores": cores, "kind": "port",
                                 "sample": sample}

@@ -107,7 +107,8 @@ void GenerateOpticalFlowDatabase(const VideoInfo& video_info, FrameAccessorFunct
             if (!kps.empty()) Check(ctx, pc_analyze_preset_keypoints(ctx, frame_id, kps[0].data(), (int)kps.size()));
         }
         if (pc_analyze_pending(ctx) >= 3) drain_one();
-        Check(ctx, pc_analyze_push_frame(ctx, frame_id, frame->data, frame->stride, PC_MEM_HOST));
+        Check(ctx, pc_analyze_push_frame(ctx, frame_id, frame->data, frame->stride,
+                                         frame->pinned ? PC_MEM_HOST_PINNED : PC_MEM_HOST));
         alive.push_back(frame->keep_alive);
     }
     while (pc_analyze_pending(ctx) > 0) drain_one();

@@ -20,6 +20,7 @@ struct Frame {
     int width = 0, height = 0;
     size_t stride = 0;
     std::shared_ptr<void> keep_alive;
+    bool pinned = false;      // `data` is page-locked (pc_host_alloc_pinned): uploaded without a staging copy
 };
 using FrameAccessorFunction = std::function<std::optional<Frame>(int32_t frame_id)>;
 using OpticalFlowProgressCallback = std::function<bool(float progress, const std::string& progress_message)>;

@@ -62,6 +62,55 @@ struct OpticalFlowRequest {
 };
 using OpticalFlowThreadMessage = std::variant<OpticalFlowProgress, OpticalFlowRequest, bool, CppException>;
 
+// Page-locked frame buffers for the OpticalFlowThread hand-off, allocated through the C ABI on the
+// process-wide solver context (page-locked memory is usable by every context of the device).
+class PinnedFrameRing {
+   public:
+    static constexpr int kFrameRing = 6;
+    ~PinnedFrameRing() { Release(); }
+    // next slot of `bytes` bytes, or nullptr if page-locked memory cannot be had
+    uint8_t* Slot(size_t bytes) {
+        if (failed_) return nullptr;
+        if (bytes != bytes_) {
+            Release();
+            try {
+                dc_ = AcquireDeviceContext(0, 0, 0);
+            } catch (...) {
+                failed_ = true;
+                return nullptr;
+            }
+            for (int i = 0; i < kFrameRing; i++) {
+                void* p = nullptr;
+                if (pc_host_alloc_pinned(dc_->ctx, bytes, &p) != PC_OK) {
+                    Release();
+                    failed_ = true;
+                    return nullptr;
+                }
+                slots_[i] = static_cast<uint8_t*>(p);
+            }
+            bytes_ = bytes;
+        }
+        uint8_t* s = slots_[next_];
+        next_ = (next_ + 1) % kFrameRing;
+        return s;
+    }
+
+   private:
+    void Release() {
+        for (auto& p : slots_) {
+            if (p && dc_) pc_host_free_pinned(dc_->ctx, p);
+            p = nullptr;
+        }
+        bytes_ = 0;
+        next_ = 0;
+    }
+    std::shared_ptr<DeviceContext> dc_;
+    uint8_t* slots_[kFrameRing] = {nullptr};
+    size_t bytes_ = 0;
+    int next_ = 0;
+    bool failed_ = false;
+};
+
 class OpticalFlowThread {
    public:
     OpticalFlowThread(VideoInfo video_info, std::string database_path, GFTTOptions detector_options = {},
@@ -86,16 +135,39 @@ class OpticalFlowThread {
     }
     std::optional<OpticalFlowThreadMessage> TryPop() { return queue_.TryPop(); }
     bool Empty() const { return queue_.Empty(); }
-    // The frame is deep-copied on the calling thread (opticalflow_thread.h:120-132).
+    // The frame is deep-copied on the calling thread (opticalflow_thread.h:120-132) -- here straight
+    // into a ring of page-locked buffers, so the upload that follows is one asynchronous DMA with no
+    // staging copy and no per-frame allocation.  A slot is reused kFrameRing frames later; the
+    // analyzer keeps at most 4 frames in flight (pipelines.cc), whose uploads finished long before.
     void ProvideFrame(int32_t frame_id, const uint8_t* rgb, int width, int height, size_t stride) {
-        auto buf = std::shared_ptr<uint8_t[]>(new uint8_t[(size_t)height * width * 3]);
-        for (int y = 0; y < height; y++) memcpy(buf.get() + (size_t)y * width * 3, rgb + (size_t)y * stride, (size_t)width * 3);
+        const size_t row = (size_t)width * 3, bytes = row * (size_t)height;
         Frame f;
-        f.data = buf.get();
         f.width = width;
         f.height = height;
-        f.stride = (size_t)width * 3;
-        f.keep_alive = buf;
+        f.stride = row;
+        uint8_t* dst = ring_.Slot(bytes);
+        if (dst) {
+            f.pinned = true;
+        } else {                                   // no page-locked memory: an ordinary copy
+            auto buf = std::shared_ptr<uint8_t[]>(new uint8_t[bytes]);
+            dst = buf.get();
+            f.keep_alive = buf;
+        }
+        f.data = dst;
+        // 4K RGB is 25 MB: split the copy over a few threads
+        const int parts = bytes >= (8u << 20) ? 4 : 1;
+        auto copy_rows = [&](int y0, int y1) {
+            if (stride == row) memcpy(dst + (size_t)y0 * row, rgb + (size_t)y0 * row, (size_t)(y1 - y0) * row);
+            else for (int y = y0; y < y1; y++) memcpy(dst + (size_t)y * row, rgb + (size_t)y * stride, row);
+        };
+        if (parts == 1) {
+            copy_rows(0, height);
+        } else {
+            std::thread helpers[3];
+            for (int k = 1; k < parts; k++) helpers[k - 1] = std::thread(copy_rows, height * k / parts, height * (k + 1) / parts);
+            copy_rows(0, height / parts);
+            for (auto& t : helpers) t.join();
+        }
         {
             std::lock_guard<std::mutex> lk(frame_mtx_);
             provided_ = std::make_pair(frame_id, std::move(f));
@@ -146,6 +218,7 @@ class OpticalFlowThread {
     const bool write_images_;
     ResultQueue<OpticalFlowThreadMessage> queue_;
     std::optional<std::pair<int32_t, Frame>> provided_;
+    PinnedFrameRing ring_;       // touched by the providing thread only
     std::mutex frame_mtx_;
     std::condition_variable frame_cv_;
     bool stop_ = false;
