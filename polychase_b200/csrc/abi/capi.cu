@@ -419,7 +419,7 @@ int pc_create(const pc_limits* limits, pc_ctx** out) {
     // one block holds every detector counter that must be zero at the start of a frame, so the init
     // launch of the min-eig stage clears them all: [0] candidate count, [8..15] select scratch,
     // then the greedy round counters, the two 4096-bin value histograms and the short list's bin cursors
-    cp->det_zero_ints = 16 + 2 * kMaxGreedyRounds + 3 * 4096;
+    cp->det_zero_ints = 16 + 3 * kMaxGreedyRounds + 3 * 4096;
     PC_CUDA(nullptr, cudaMalloc(&cp->det_zero, sizeof(int) * cp->det_zero_ints));
     PC_CUDA(nullptr, cudaMemset(cp->det_zero, 0, sizeof(int) * cp->det_zero_ints));
     cp->cand_count = cp->det_zero;
@@ -430,7 +430,7 @@ int pc_create(const pc_limits* limits, pc_ctx** out) {
     PC_CUDA(nullptr, cudaMalloc(&cp->sel.sorted, sizeof(unsigned long long) * cp->sel.sorted_cap));
     cp->sel.sel = cp->det_zero + 8;
     cp->sel.round_counters = cp->det_zero + 16;
-    cp->sel.hist = cp->sel.round_counters + 2 * kMaxGreedyRounds;
+    cp->sel.hist = cp->sel.round_counters + 3 * kMaxGreedyRounds;
     cp->sel.kept_hist = cp->sel.hist + 4096;
     cp->sel.bin_cursor = cp->sel.kept_hist + 4096;
     PC_CUDA(nullptr, cudaMalloc(&cp->sel.bin_start, sizeof(int) * 4096));

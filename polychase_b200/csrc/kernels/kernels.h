@@ -57,7 +57,7 @@ struct SelectWorkspace {
     unsigned long long* sorted;        // sorted_cap >= cap entries (CUB sort output, unlimited path)
     unsigned long long* strong;        // cap entries: the strongest candidates (max_corners > 0 path)
     int* accepted_count;               // device int
-    int* round_counters;               // 2 * kMaxGreedyRounds ints
+    int* round_counters;               // 3 * kMaxGreedyRounds ints (one set per fixed-point run of a launch)
     int* remaining;                    // device int: undecided candidates left (0 = converged)
     int* hist;                         // 4096 ints: 12-bit value histogram of all candidates (written by K5)
     int* kept_hist;                    // 4096 ints: 12-bit value histogram of kept keys
@@ -68,7 +68,7 @@ struct SelectWorkspace {
     int cap;
     int sorted_cap;
 };
-constexpr int kMaxGreedyRounds = 2048;
+constexpr int kMaxGreedyRounds = 1024;   // per fixed-point run; a round resolves ~100 dependency levels
 size_t select_cub_temp_bytes(int cap);
 // Runs suppression over `cand` (count on device), sorts accepted keys descending and writes
 // min(accepted, max_corners) keypoints (x,y floats) + their count.

@@ -281,37 +281,39 @@ __global__ void __launch_bounds__(LK_WARPS * 32) lk_kernel(LKBatch batch, LKPara
     }
 }
 
-// K9: order-preserving compaction of status==1 rows (one block per pair).  A thread owns
-// CP_PER consecutive rows of each 1024 * CP_PER chunk: one warp-shuffle scan + one shared-memory
-// pass over the 32 warp totals per chunk.
+// K9: order-preserving compaction of status==1 rows (one block per pair).  A warp owns CP_PER * 32
+// consecutive rows of each 1024 * CP_PER chunk and reads them as CP_PER coalesced groups of 32 (a
+// thread owning CP_PER consecutive rows would make every warp load touch 32 different lines: one SM's
+// L1 then bounds the kernel); slots come from ballots inside the warp and one shared-memory pass over
+// the 32 warp totals per chunk.
 constexpr int CP_PER = 8;
 __global__ void __launch_bounds__(1024) lk_compact_kernel(LKBatch batch) {
     const LKPair& pr = batch.pair[blockIdx.x];
     __shared__ int warp_tot[2][32];
     const int n = min(*pr.n_pts, batch.cap);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const unsigned lt = (1u << lane) - 1;
     int base = 0, buf = 0;
     for (int start = 0; start < n; start += 1024 * CP_PER, buf ^= 1) {
-        const int i0 = start + threadIdx.x * CP_PER;
-        unsigned keep = 0;
-        if (i0 + CP_PER <= n && (reinterpret_cast<uintptr_t>(pr.status) & 7) == 0) {
-            const uint2 sv = __ldg(reinterpret_cast<const uint2*>(pr.status + i0));
+        const int w0 = start + wid * (32 * CP_PER);          // first row of this warp
+        unsigned bal[CP_PER];
+        float2 t[CP_PER];
+        float e[CP_PER];
+        int mine = 0;                                        // rows kept by the warp (uniform)
 #pragma unroll
-            for (int k = 0; k < CP_PER; k++)
-                if ((((k < 4 ? sv.x : sv.y) >> (8 * (k & 3))) & 0xffu) == 1u) keep |= 1u << k;
-        } else {
-#pragma unroll
-            for (int k = 0; k < CP_PER; k++)
-                if (i0 + k < n && pr.status[i0 + k] == 1) keep |= 1u << k;
+        for (int k = 0; k < CP_PER; k++) {
+            const int i = w0 + 32 * k + lane;
+            const bool keep = i < n && pr.status[i] == 1;
+            bal[k] = __ballot_sync(0xffffffffu, keep);
+            mine += __popc(bal[k]);
+            t[k] = make_float2(0.f, 0.f);
+            e[k] = 0.f;
+            if (keep) {                                      // every load before the first store
+                t[k] = __ldg(reinterpret_cast<const float2*>(pr.next + 2 * i));
+                e[k] = __ldg(pr.err + i);
+            }
         }
-        const int mine = __popc(keep);
-        int incl = mine;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int v = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += v;
-        }
-        if (lane == 31) warp_tot[buf][wid] = incl;
+        if (lane == 0) warp_tot[buf][wid] = mine;
         __syncthreads();
         const int wt = warp_tot[buf][lane];                  // 32 warps: one total per lane
         int wincl = wt;
@@ -320,30 +322,17 @@ __global__ void __launch_bounds__(1024) lk_compact_kernel(LKBatch batch) {
             const int v = __shfl_up_sync(0xffffffffu, wincl, o);
             if (lane >= o) wincl += v;
         }
-        const int before = __shfl_sync(0xffffffffu, wincl - wt, wid);
+        int slot = base + __shfl_sync(0xffffffffu, wincl - wt, wid);
         const int total = __shfl_sync(0xffffffffu, wincl, 31);
-        int slot = base + before + incl - mine;
-        // every load before the first store: the outputs may alias the inputs as far as the compiler
-        // knows, and a load -> store -> load chain costs one L2 round trip per row
-        float2 t[CP_PER];
-        float e[CP_PER];
 #pragma unroll
         for (int k = 0; k < CP_PER; k++) {
-            t[k] = make_float2(0.f, 0.f);
-            e[k] = 0.f;
-            if (keep & (1u << k)) {
-                t[k] = __ldg(reinterpret_cast<const float2*>(pr.next + 2 * (i0 + k)));
-                e[k] = __ldg(pr.err + i0 + k);
+            if (bal[k] & (1u << lane)) {
+                const int s = slot + __popc(bal[k] & lt);
+                pr.out_idx[s] = (uint32_t)(w0 + 32 * k + lane);
+                *reinterpret_cast<float2*>(pr.out_tgt + 2 * s) = t[k];
+                pr.out_err[s] = e[k];
             }
-        }
-#pragma unroll
-        for (int k = 0; k < CP_PER; k++) {
-            if (keep & (1u << k)) {
-                pr.out_idx[slot] = (uint32_t)(i0 + k);
-                *reinterpret_cast<float2*>(pr.out_tgt + 2 * slot) = t[k];
-                pr.out_err[slot] = e[k];
-                slot++;
-            }
+            slot += __popc(bal[k]);
         }
         base += total;
     }

@@ -35,7 +35,7 @@ namespace cg = cooperative_groups;
 namespace pc {
 
 enum : uint8_t { ST_NONE = 0, ST_UNDECIDED = 1, ST_KEPT = 2, ST_REJECTED = 3 };
-constexpr int kGreedySpins = 96;      // polls of a blocked candidate's blockers (~0.7 us each) before it waits for the next round
+constexpr int kGreedySpins = 256;     // polls of a blocked candidate's blockers (~0.5 us each) before it waits for the next round
 
 __device__ __forceinline__ unsigned long long key_at(const float* __restrict__ eig, int eig_pitch, int w, int x,
                                                      int y) {
@@ -47,7 +47,7 @@ __device__ __forceinline__ unsigned long long key_at(const float* __restrict__ e
 // 9 rows x 3 aligned words that cover the disc's bounding box are loaded up front
 // (independent L2 loads), then only the non-zero state bytes are looked at.
 constexpr int kMaxBlockers = 4;
-__device__ __forceinline__ int decide(unsigned long long key, int x, int y, const float* __restrict__ eig,
+__device__ __noinline__ int decide_scan(unsigned long long key, int x, int y, const float* __restrict__ eig,
                                       int eig_pitch, const uint8_t* state, int state_pitch, int w, int h, int R,
                                       double md2, int (&blockers)[kMaxBlockers], int& num_blockers) {
     bool blocked = false;
@@ -110,6 +110,80 @@ __device__ __forceinline__ int decide(unsigned long long key, int x, int y, cons
             }
         }
     }
+    return blocked ? 0 : ST_KEPT;
+}
+
+// Front end of decide_scan for R <= 4.  A warp executes the union of its lanes' neighbour loops, so a
+// load of the neighbour's eigenvalue inside those loops (one L2 round trip each, one after the other)
+// made a warp's 32 candidates cost ~40 us.  Here the loops only collect the (few) decided-or-pending
+// neighbours inside the disc; their eigenvalues are then fetched with independent loads and compared.
+constexpr int kMaxNbr = 12;
+__device__ __forceinline__ int decide(unsigned long long key, int x, int y, const float* __restrict__ eig,
+                                      int eig_pitch, const uint8_t* state, int state_pitch, int w, int h, int R,
+                                      double md2, int (&blockers)[kMaxBlockers], int& num_blockers) {
+    if (R > 4) return decide_scan(key, x, y, eig, eig_pitch, state, state_pitch, w, h, R, md2, blockers, num_blockers);
+    num_blockers = 0;
+    const int xl = x - 4, wx0 = xl & ~3;                     // may be negative: masked below
+    uint32_t wd[9][3];
+#pragma unroll
+    for (int r = 0; r < 9; r++) {
+        const int ny = y - 4 + r;
+        const bool row_ok = (unsigned)ny < (unsigned)h;
+        const uint8_t* row = state + (size_t)(row_ok ? ny : y) * state_pitch;
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            const int wx = wx0 + 4 * k;
+            wd[r][k] = (row_ok && wx >= 0 && wx < state_pitch) ? __ldcg(reinterpret_cast<const uint32_t*>(row + wx)) : 0u;
+        }
+    }
+    int nbr[kMaxNbr];                                        // (dy + 4) << 20 | nx << 4 | state
+    int cnt = 0;
+#pragma unroll
+    for (int r = 0; r < 9; r++) {
+        const int dy = r - 4;
+        if (dy < -R || dy > R) continue;
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            uint32_t v = wd[r][k];
+            while (v) {
+                const int b = (__ffs(v) - 1) >> 3;
+                const uint32_t ns = (v >> (8 * b)) & 0xffu;
+                v &= ~(0xffu << (8 * b));
+                const int nx = wx0 + 4 * k + b, dx = nx - x;
+                if (dx < -R || dx > R || (dx == 0 && dy == 0) || nx < 0 || nx >= w) continue;
+                if ((double)(dx * dx + dy * dy) >= md2) continue;
+                if (ns != ST_UNDECIDED && ns != ST_KEPT) continue;
+                if (cnt < kMaxNbr) nbr[cnt] = (r << 20) | (nx << 4) | (int)ns;
+                cnt++;
+            }
+        }
+    }
+    if (cnt > kMaxNbr)                                       // a crowd: the sequential scan handles any count
+        return decide_scan(key, x, y, eig, eig_pitch, state, state_pitch, w, h, R, md2, blockers, num_blockers);
+    float ev[kMaxNbr];
+#pragma unroll
+    for (int i = 0; i < kMaxNbr; i++) {
+        ev[i] = 0.f;
+        if (i < cnt) {
+            const int ny = y - 4 + (nbr[i] >> 20), nx = (nbr[i] >> 4) & 0xffff;
+            ev[i] = eig[(size_t)ny * eig_pitch + nx];
+        }
+    }
+    bool blocked = false, rejected = false;
+#pragma unroll
+    for (int i = 0; i < kMaxNbr; i++) {
+        if (i < cnt) {
+            const int ny = y - 4 + (nbr[i] >> 20), nx = (nbr[i] >> 4) & 0xffff;
+            const unsigned long long nkey = ((unsigned long long)float_to_ordered_uint(ev[i]) << 32) | (unsigned)(ny * w + nx);
+            if (nkey > key) {
+                if ((nbr[i] & 0xf) == ST_KEPT) rejected = true;
+                blocked = true;
+                if (num_blockers < kMaxBlockers) blockers[num_blockers] = ny * state_pitch + nx;
+                num_blockers++;
+            }
+        }
+    }
+    if (rejected) return ST_REJECTED;
     return blocked ? 0 : ST_KEPT;
 }
 
@@ -197,13 +271,19 @@ __device__ __forceinline__ int greedy_rounds(cg::grid_group& grid, int* block_un
                 if (__ldcg(sp) == ST_UNDECIDED) {
                     int blockers[kMaxBlockers], nb;
                     d = decide(key, x, y, eig, eig_pitch, state, state_pitch, w, h, R, md2, blockers, nb);
+                    // Publish a decision the moment it exists, BEFORE any code that waits: the lanes of a
+                    // warp reconverge after the polling loop below, so a store placed behind it would be
+                    // held back until the warp's slowest lane stops polling -- and that lane may be
+                    // polling for exactly this store.
+                    if (d == ST_REJECTED) *(volatile uint8_t*)sp = ST_REJECTED;
+                    else if (d == ST_KEPT) *(volatile uint8_t*)sp = ST_KEPT;
                     if (d == 0 && nb <= kMaxBlockers) {
                         // The blockers are stronger candidates that other (co-resident) threads are deciding
                         // right now: watch just those few state bytes for a bounded time instead of paying
                         // a grid barrier + rescan per dependency level.  States only move UNDECIDED -> final,
                         // so "a blocker got KEPT" / "all blockers got REJECTED" are final answers too.
                         for (int spin = 0; spin < kGreedySpins && d == 0; spin++) {
-                            __nanosleep(100);
+                            __nanosleep(40);
                             bool pending = false;
                             for (int k = 0; k < nb; k++) {
                                 const uint8_t ns = __ldcg(state + blockers[k]);
@@ -211,12 +291,10 @@ __device__ __forceinline__ int greedy_rounds(cg::grid_group& grid, int* block_un
                                 else if (ns == ST_UNDECIDED) pending = true;
                             }
                             if (d == 0 && !pending) d = ST_KEPT;
+                            if (d != 0) *(volatile uint8_t*)sp = (uint8_t)d;     // published inside the loop
                         }
                     }
-                    // publish the decision at once: other threads are polling this byte
-                    if (d == ST_REJECTED) *(volatile uint8_t*)sp = ST_REJECTED;
-                    else if (d == ST_KEPT) *(volatile uint8_t*)sp = ST_KEPT;
-                    else undecided++;
+                    if (d == 0) undecided++;
                 }
             }
             // the list append can wait for the warp to reconverge: one atomic per warp, not per corner
@@ -243,57 +321,73 @@ __device__ __forceinline__ int greedy_rounds(cg::grid_group& grid, int* block_un
 }
 
 // The whole suppression stage in one cooperative launch.
-//   strong_want == 0 (max_corners == 0): one fixed-point run over every candidate.
-//   strong_want  > 0: (1) the candidates at or above the value bin at which the suffix count of the
-//   NMS histogram reaches strong_want are appended to `strong` (every block recomputes that bin:
-//   4096 ints); (2) fixed point over `strong`; (3) only if that kept fewer than max_corners corners,
-//   a second run over everything (decided candidates are skipped through the state map).
+//   max_corners == 0: one fixed-point run over every candidate.
+//   max_corners  > 0: the reference returns the max_corners strongest kept corners, and a decision only
+//   depends on stronger candidates, so the fixed point is run on value-closed prefixes of the candidate
+//   set: first the candidates at or above the value bin at which the suffix count of the NMS histogram
+//   reaches 1.5 x max_corners (on textured frames suppression removes few of the strongest corners:
+//   8 466 candidates give 8 000 kept corners at 4K), then the band down to 4 x max_corners, then
+//   everything, stopping as soon as max_corners corners are kept.  Every block recomputes the bins
+//   (4096 ints); each stage appends its band of the candidate list to `strong`.
 __global__ void __launch_bounds__(256) greedy_suppress_kernel(
     const unsigned long long* __restrict__ cand, const int* __restrict__ cand_count, int cand_cap,
     const float* __restrict__ eig, int eig_pitch, uint8_t* state, int state_pitch, int w, int h, int R,
     double md2, unsigned long long* __restrict__ accepted, int* accepted_count, int* kept_hist, int* round_counters,
-    int* remaining, const int* value_hist, int strong_want, unsigned long long* __restrict__ strong,
-    int* strong_count, int max_corners) {
+    int* remaining, const int* value_hist, unsigned long long* __restrict__ strong, int* strong_count,
+    int max_corners) {
     cg::grid_group grid = cg::this_grid();
     __shared__ int block_undecided;
     __shared__ int s_warp[8], s_res[8];
     const int n = min(*cand_count, cand_cap);
     const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
-    int last;
-    if (strong_want > 0) {
-        int strong_total;
-        const unsigned thr = (unsigned)suffix_threshold_bin<256, 16>(value_hist, strong_want, s_warp, s_res, &strong_total);
-        // append with one global atomic per block and chunk: slots inside the block from the warp counts
+    int last = 0;
+    if (max_corners > 0) {
         const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-        for (int base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
-            const int i = base + threadIdx.x;
-            unsigned long long key = 0;
-            bool keep = false;
-            if (i < n) {
-                key = cand[i];
-                keep = (unsigned)(key >> 52) >= thr;
-            }
-            const unsigned m = __ballot_sync(0xffffffffu, keep);
-            if (lane == 0) s_warp[wid] = __popc(m);
-            __syncthreads();
-            if (threadIdx.x == 0) {
-                int tot = 0;
+        const long long wants[2] = {(long long)max_corners + max_corners / 2, 4ll * max_corners};
+        unsigned above = 0xffffffffu;                        // bins >= `above` were handled by an earlier stage
+        int list_begin = 0;
+        bool enough = false;
+        for (int stage = 0; stage < 2 && !enough && above > 0; stage++) {
+            int total;
+            const int want = (int)min(wants[stage], (long long)n);
+            const unsigned thr = (unsigned)suffix_threshold_bin<256, 16>(value_hist, want, s_warp, s_res, &total);
+            __syncthreads();                                 // s_warp / s_res are reused below
+            // append this stage's band with one global atomic per block and chunk
+            for (int base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
+                const int i = base + threadIdx.x;
+                unsigned long long key = 0;
+                bool keep = false;
+                if (i < n) {
+                    key = cand[i];
+                    const unsigned bin = (unsigned)(key >> 52);
+                    keep = bin >= thr && bin < above;
+                }
+                const unsigned m = __ballot_sync(0xffffffffu, keep);
+                if (lane == 0) s_warp[wid] = __popc(m);
+                __syncthreads();
+                if (threadIdx.x == 0) {
+                    int tot = 0;
 #pragma unroll
-                for (int q = 0; q < 8; q++) { const int c = s_warp[q]; s_warp[q] = tot; tot += c; }
-                s_res[0] = tot ? atomicAdd(strong_count, tot) : 0;
+                    for (int q = 0; q < 8; q++) { const int c = s_warp[q]; s_warp[q] = tot; tot += c; }
+                    s_res[0] = tot ? atomicAdd(strong_count, tot) : 0;
+                }
+                __syncthreads();
+                if (keep) strong[s_res[0] + s_warp[wid] + __popc(m & ((1u << lane) - 1))] = key;
+                __syncthreads();
             }
-            __syncthreads();
-            if (keep) strong[s_res[0] + s_warp[wid] + __popc(m & ((1u << lane) - 1))] = key;
-            __syncthreads();
+            grid.sync();
+            const int list_end = min(*((volatile int*)strong_count), cand_cap);
+            last = greedy_rounds(grid, &block_undecided, strong + list_begin, list_end - list_begin, eig, eig_pitch, state,
+                                 state_pitch, w, h, R, md2, accepted, accepted_count, kept_hist,
+                                 round_counters + stage * kMaxGreedyRounds);
+            // every block is past the barrier of the last round: the kept count is final and uniform
+            enough = *((volatile int*)accepted_count) >= max_corners;
+            list_begin = list_end;
+            above = thr;
         }
-        grid.sync();
-        const int n1 = min(*((volatile int*)strong_count), cand_cap);
-        last = greedy_rounds(grid, &block_undecided, strong, n1, eig, eig_pitch, state, state_pitch, w, h, R, md2,
-                             accepted, accepted_count, kept_hist, round_counters);
-        // every block is past the barrier of the last round: the kept count is final and uniform
-        if (*((volatile int*)accepted_count) < max_corners)
+        if (!enough && above > 0)                            // candidates below the last band remain
             last = greedy_rounds(grid, &block_undecided, cand, n, eig, eig_pitch, state, state_pitch, w, h, R, md2,
-                                 accepted, accepted_count, kept_hist, round_counters + kMaxGreedyRounds);
+                                 accepted, accepted_count, kept_hist, round_counters + 2 * kMaxGreedyRounds);
     } else {
         last = greedy_rounds(grid, &block_undecided, cand, n, eig, eig_pitch, state, state_pitch, w, h, R, md2,
                              accepted, accepted_count, kept_hist, round_counters);
@@ -440,8 +534,7 @@ size_t select_cub_temp_bytes(int cap) {
 
 static void launch_greedy(const unsigned long long* cand, const int* cand_count, int cand_cap, const float* eig,
                           int eig_pitch, uint8_t* state, int state_pitch, int w, int h, double min_distance,
-                          const SelectWorkspace& ws, int* kept_hist, int strong_want, int max_corners, int sm_count,
-                          cudaStream_t s) {
+                          const SelectWorkspace& ws, int* kept_hist, int max_corners, int sm_count, cudaStream_t s) {
     int R = (int)ceil(min_distance) - 1;
     double md2 = min_distance * min_distance;
     static int blocks_per_sm = 0;
@@ -457,8 +550,7 @@ static void launch_greedy(const unsigned long long* cand, const int* cand_count,
     void* args[] = {(void*)&cand, (void*)&cand_count, (void*)&cand_cap, (void*)&eig, (void*)&eig_pitch, (void*)&state,
                     (void*)&state_pitch, (void*)&w, (void*)&h, (void*)&R, (void*)&md2, (void*)&ws.accepted,
                     (void*)&ws.accepted_count, (void*)&kept_hist, (void*)&round_counters, (void*)&ws.remaining,
-                    (void*)&value_hist, (void*)&strong_want, (void*)&strong, (void*)&strong_count,
-                    (void*)&max_corners};
+                    (void*)&value_hist, (void*)&strong, (void*)&strong_count, (void*)&max_corners};
     cudaLaunchCooperativeKernel((void*)greedy_suppress_kernel, dim3(nblocks), dim3(256), args, 0, s);
 }
 
@@ -473,9 +565,8 @@ void launch_select(const unsigned long long* cand, const int* cand_count, int ca
     // the unlimited path sorts the whole accepted[] buffer: unused slots must be zero (they sort last)
     if (!limited) cudaMemsetAsync(ws.accepted, 0, sizeof(unsigned long long) * (size_t)ws.cap, s);
     if (min_distance >= 1.0) {
-        // limited: first the strongest ~4*max_corners candidates, everything only if that is not enough
         launch_greedy(cand, cand_count, cand_cap, eig, eig_pitch, state, state_pitch, w, h, min_distance, ws, kept_hist,
-                      limited ? 4 * max_corners : 0, max_corners, sm_count, s);
+                      limited ? max_corners : 0, sm_count, s);
     } else {
         accept_all_kernel<<<sm_count * 2, 256, 0, s>>>(cand, cand_count, cand_cap, ws.accepted, ws.accepted_count,
                                                        kept_hist, ws.remaining);
