@@ -6,7 +6,7 @@
 //
 // The tracker is a sequential chain of small problems (<= 8 sources x max_features matches, a
 // dozen LM iterations each), so the kernel is built for LATENCY, not bandwidth:
-//   * one thread-block cluster (8 CTAs, 16 when allowed) owns the problem.  The matches are staged
+//   * one thread-block cluster (16 CTAs where the device can place one, else 8) owns the problem.  The matches are staged
 //     once into shared memory as structure-of-arrays (ray misses / zero weights folded into one
 //     weight array) and never re-read from global memory;
 //   * every reduction (cost, or the lower triangle of JtJ + Jtr) is a transposing warp reduction
@@ -38,6 +38,7 @@ constexpr int PNP_WARPS = PNP_THREADS / 32;
 constexpr int PNP_MAXACC = 64;       // two groups of 32 values
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int PNP_STAGE_ARRAYS = 6;  // X0 X1 X2 x0 x1 weight
+constexpr unsigned PNP_MAX_CLUSTER = 16;
 
 struct PnpShared {
     double warp_part[PNP_WARPS][PNP_MAXACC];
@@ -95,9 +96,17 @@ __device__ __forceinline__ void cluster_reduce(PnpShared& sh, int& parity, const
     }
     cluster.sync();                                  // partials of every CTA are visible
     if (threadIdx.x < N) {
-        double s = 0.0;
+        // all remote reads in flight at once (a rolled loop pays one DSMEM round trip per peer), then
+        // the sum in rank order so that every CTA gets the same bits
         const unsigned nb = cluster.num_blocks();
-        for (unsigned r = 0; r < nb; r++) s += *cluster.map_shared_rank(&sh.part[parity][threadIdx.x], r);
+        double part[PNP_MAX_CLUSTER];
+#pragma unroll
+        for (unsigned r = 0; r < PNP_MAX_CLUSTER; r++)
+            part[r] = r < nb ? *cluster.map_shared_rank(&sh.part[parity][threadIdx.x], r) : 0.0;
+        double s = 0.0;
+#pragma unroll
+        for (unsigned r = 0; r < PNP_MAX_CLUSTER; r++)
+            if (r < nb) s += part[r];
         sh.total[threadIdx.x] = s;
     }
     parity ^= 1;                                     // the next reduction publishes into the other buffer
@@ -216,13 +225,16 @@ pnp_lm_kernel(const float* __restrict__ X, const float* __restrict__ x, const fl
 #pragma unroll
     for (int k = 0; k < NP; k++) { diag[k] = 0.f; Jtr[k] = 0.f; }
 
-    for (it = 0; it < prm.max_iterations; ++it) {
-        if (rebuild) {
-            // BuildNormalEquations (lev_marq.h:231-297) with PnPProblem::EvaluateWithJacobian
-            const Cam c = make_cam(cam);
-            float acc[NACC];
+    // One pass over the matches at `cs`: the lower triangle of JtJ, Jtr (BuildNormalEquations,
+    // lev_marq.h:231-297, with PnPProblem::EvaluateWithJacobian) AND the total cost, reduced together.
+    // The LM loop evaluates every candidate step with it: when the step is accepted (the common case)
+    // the normal equations of the next iteration are already there, so an iteration costs one pass
+    // and one cluster reduction instead of two of each.  The sums are those of the separate passes.
+    auto build_at = [&](const pc_camera_state& cs) {
+            const Cam c = make_cam(cs);
+            float acc[NACC + 1];
 #pragma unroll
-            for (int k = 0; k < NACC; k++) acc[k] = 0.f;
+            for (int k = 0; k < NACC + 1; k++) acc[k] = 0.f;
             for (int k = 0; k < per_thread; k++) {
                 const Match mt = fetch(k);
                 if (mt.wt == 0.f) continue;
@@ -231,6 +243,11 @@ pnp_lm_kernel(const float* __restrict__ X, const float* __restrict__ x, const fl
                 const float iz = 1.f / Z.z;
                 const float rx = c.fx * Z.x / Z.z + c.cx - mt.u;
                 const float ry = c.fy * Z.y / Z.z + c.cy - mt.v;
+                {                                            // TotalCost of the same point (see cost_of)
+                    float r2 = rx * rx + ry * ry;
+                    if (is_behind(c, Z)) r2 = INFINITY;
+                    acc[NACC] += mt.wt * loss_value(loss, r2);
+                }
                 // dz/dZ (types.h:79-85)
                 const float a00 = c.fx * iz, a02 = -c.fx * Z.x / (Z.z * Z.z);
                 const float a11 = c.fy * iz, a12 = -c.fy * Z.y / (Z.z * Z.z);
@@ -270,7 +287,14 @@ pnp_lm_kernel(const float* __restrict__ X, const float* __restrict__ x, const fl
 #pragma unroll
                 for (int r = 0; r < NP; r++) acc[NJ + r] += J0[r] * wrx + J1[r] * wry;
             }
-            cluster_reduce<NACC>(sh, parity, acc);
+            cluster_reduce<NACC + 1>(sh, parity, acc);
+    };
+
+    bool built = false;                              // sh.total holds the normal equations of `cam`
+    for (it = 0; it < prm.max_iterations; ++it) {
+        if (rebuild) {
+            if (!built) build_at(cam);
+            built = false;
             float g2 = 0.f;
 #pragma unroll
             for (int k = 0; k < NJ; k++) A[k] = (float)sh.total[k];
@@ -342,7 +366,8 @@ pnp_lm_kernel(const float* __restrict__ X, const float* __restrict__ x, const fl
             for (int r = 0; r < 9; r++) dp[r] = r < NP ? step[r < NP ? r : 0] : 0.f;
             camera_step(cam, dp, opt_f, opt_pp, prm.bounds, cam_new);          // pnp_problem.h:101-131
         }
-        const float cost_new = cost_of(cam_new, false);
+        build_at(cam_new);                                      // cost of the step + (speculatively) its normal equations
+        const float cost_new = (float)sh.total[NACC];
         if (cost_new < cost) {                                  // lev_marq.h:179-203
             const float actual = cost_new - cost;
             // step^T (2 Jtr + JtJ_sym(undamped, clamped diag) step)
@@ -365,6 +390,7 @@ pnp_lm_kernel(const float* __restrict__ X, const float* __restrict__ x, const fl
             cost = cost_new;
             v = 2.f;
             rebuild = true;
+            built = true;                                       // sh.total: nothing has been reduced since
         } else {
             invalid_steps++;
             if (lambda == prm.max_lambda) break;
@@ -414,7 +440,10 @@ size_t g_pnp_dyn_max = 0;
 
 int pnp_cluster_size() {
     if (g_pnp_cluster) return g_pnp_cluster;
-    int want = 8;                                               // portable maximum
+    // 16 CTAs (the non-portable maximum, allowed on sm_100) when the device can place such a cluster,
+    // else the portable 8: the solve is a latency chain, and the per-iteration pass over the matches
+    // halves with twice the CTAs (16.3 vs 21.0 ms per 32 frames in the 4K pipeline)
+    int want = 16;
     if (const char* e = getenv("PC_PNP_CLUSTER")) {
         const int vv = atoi(e);
         if (vv == 1 || vv == 2 || vv == 4 || vv == 8 || vv == 16) want = vv;
@@ -426,6 +455,23 @@ int pnp_cluster_size() {
         cudaError_t e1 = cudaFuncSetAttribute(pnp_lm_kernel<6>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
         cudaError_t e2 = cudaFuncSetAttribute(pnp_lm_kernel<9>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
         if (e1 != cudaSuccess || e2 != cudaSuccess) { cudaGetLastError(); want = 8; }
+        if (want > 8) {                                         // can a 16-CTA cluster be resident at all?
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(want);
+            cfg.blockDim = dim3(PNP_THREADS);
+            cfg.dynamicSmemBytes = 96 * 1024;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = want;
+            attr[0].val.clusterDim.y = 1;
+            attr[0].val.clusterDim.z = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = 1;
+            int n6 = 0, n9 = 0;
+            const cudaError_t q1 = cudaOccupancyMaxActiveClusters(&n6, pnp_lm_kernel<6>, &cfg);
+            const cudaError_t q2 = cudaOccupancyMaxActiveClusters(&n9, pnp_lm_kernel<9>, &cfg);
+            if (q1 != cudaSuccess || q2 != cudaSuccess || n6 < 1 || n9 < 1) { cudaGetLastError(); want = 8; }
+        }
     }
     g_pnp_cluster = want;
     return want;
