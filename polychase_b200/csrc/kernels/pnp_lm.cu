@@ -161,22 +161,17 @@ pnp_lm_kernel(const float* __restrict__ X, const float* __restrict__ x, const fl
 
     // ---- stage the matches, count the usable ones (rays that hit), initial cost --------------
     // (the weight == 0 skip is lev_marq.h:333-336)
-    auto cost_of = [&](const pc_camera_state& cs, bool first_pass) {
+    auto first_cost = [&](const pc_camera_state& cs) {
         const Cam c = make_cam(cs);
         float acc = 0.f, cnt = 0.f;
         for (int k = 0; k < per_thread; k++) {
-            Match mt;
-            if (first_pass) {
-                mt = fetch_global(k);
-                const int i = (k * (int)nblocks + (int)rank) * PNP_THREADS + tid;
-                if (i < m && (!valid || valid[i])) cnt += 1.f;
-                if (staged) {
-                    const int j = k * PNP_THREADS + tid;
-                    stage[j] = mt.X0; stage[per_cta + j] = mt.X1; stage[2 * per_cta + j] = mt.X2;
-                    stage[3 * per_cta + j] = mt.u; stage[4 * per_cta + j] = mt.v; stage[5 * per_cta + j] = mt.wt;
-                }
-            } else {
-                mt = fetch(k);
+            const Match mt = fetch_global(k);
+            const int i = (k * (int)nblocks + (int)rank) * PNP_THREADS + tid;
+            if (i < m && (!valid || valid[i])) cnt += 1.f;
+            if (staged) {
+                const int j = k * PNP_THREADS + tid;
+                stage[j] = mt.X0; stage[per_cta + j] = mt.X1; stage[2 * per_cta + j] = mt.X2;
+                stage[3 * per_cta + j] = mt.u; stage[4 * per_cta + j] = mt.v; stage[5 * per_cta + j] = mt.wt;
             }
             if (mt.wt == 0.f) continue;
             // PnPProblem::Evaluate (pnp_problem.h:52-61)
@@ -188,16 +183,11 @@ pnp_lm_kernel(const float* __restrict__ X, const float* __restrict__ x, const fl
             acc += mt.wt * loss_value(loss, r2);
         }
         const float two[2] = {acc, cnt};
-        if (first_pass) {
-            cluster_reduce<2>(sh, parity, two);
-        } else {
-            const float one[1] = {acc};
-            cluster_reduce<1>(sh, parity, one);
-        }
+        cluster_reduce<2>(sh, parity, two);
         return (float)sh.total[0];
     };
 
-    float cost = cost_of(cam, true);
+    float cost = first_cost(cam);
     const int n_valid = (int)sh.total[1];
     if (lead) {
         result->num_matches = n_valid;
@@ -243,7 +233,7 @@ pnp_lm_kernel(const float* __restrict__ X, const float* __restrict__ x, const fl
                 const float iz = 1.f / Z.z;
                 const float rx = c.fx * Z.x / Z.z + c.cx - mt.u;
                 const float ry = c.fy * Z.y / Z.z + c.cy - mt.v;
-                {                                            // TotalCost of the same point (see cost_of)
+                {                                            // TotalCost of the same point (as in first_cost)
                     float r2 = rx * rx + ry * ry;
                     if (is_behind(c, Z)) r2 = INFINITY;
                     acc[NACC] += mt.wt * loss_value(loss, r2);

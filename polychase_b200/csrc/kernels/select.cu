@@ -11,17 +11,18 @@
 // formulation: a candidate becomes REJECTED as soon as a stronger in-disc candidate is
 // KEPT, and KEPT once every stronger in-disc candidate is decided and none is kept.
 // A persistent cooperative kernel iterates that to its fixed point (grid-wide barrier per
-// round, no host round trips); the dependency depth measured on 4K frames is <= 10 rounds.
+// round, no host round trips); blocked candidates poll their few blockers inside a round, so on 4K
+// frames one round decides everything.
 //
 // With max_corners > 0 the reference stops after max_corners kept corners (gftt.cc:160-162),
 // i.e. it returns a prefix of the unlimited result.  Because decisions only depend on stronger
-// candidates, the fixed point is first run on the strongest ~4*max_corners candidates (a value
-// threshold from a 12-bit histogram); only if that yields fewer than max_corners kept corners
-// does a second pass process everything.  Kept keys are counted into a 12-bit-bin histogram
-// of their value as they are accepted; compact_top_kernel finds the bin that holds the
-// max_corners-th strongest key and gathers the keys at or above it (max_corners plus part of one
-// bin); select_rank_emit_kernel stages that short list in shared memory and ranks it by counting
-// ((value, address) descending): rank r < max_corners is keypoint r.
+// candidates, the fixed point is run on value-closed prefixes of the candidate set (value
+// thresholds from the 12-bit histogram the NMS kernel fills): the strongest ~1.5*max_corners, then
+// down to ~4*max_corners, then everything, stopping once max_corners corners are kept.  Kept keys
+// are counted into a 12-bit-bin histogram of their value as they are accepted; compact_top_kernel
+// finds the bin that holds the max_corners-th strongest key and scatters the keys at or above it
+// (max_corners plus part of one bin) grouped by bin; select_rank_emit_kernel ranks every key inside
+// its bin group ((value, address) descending): rank r < max_corners is keypoint r.
 // With max_corners == 0 every kept key is sorted (CUB radix sort).
 #include <algorithm>
 #include <cooperative_groups.h>
