@@ -307,7 +307,7 @@ def main():
     # ---- Track (tracker.cc:36-213): the forward PnP sweep, chained on the device behind the analyzer
     # (pc_analyze_track_begin): each frame's ray cast + LM solve is queued right after its LK batch
     # and reads the flow rows / source poses where they already are in HBM.
-    bundle = capi.default_bundle()
+    bundle = capi.default_bundle(loss_type=2)          # Cauchy: what the addon passes (blender_addon/operators/tracking.py:209)
     model = np.eye(4, dtype=np.float32)
     if track:
         verts, tris = synth.plane_mesh(w, h, scale)
@@ -322,6 +322,7 @@ def main():
             self.matches = 0
             self.iterations = 0
             self.max_t_err = 0.0
+            self.trace = []
 
         def truth(self, idx: int):
             i = image_of(idx, self.ring)
@@ -335,7 +336,11 @@ def main():
             self.matches += r["num_matches"]
             self.iterations += r["stats"].iterations
             i = image_of(idx, self.ring)
-            self.max_t_err = max(self.max_t_err, float(np.abs(np.array(r["camera"].t[:]) - ts[i]).max()))
+            e = float(np.abs(np.array(r["camera"].t[:]) - ts[i]).max())
+            self.max_t_err = max(self.max_t_err, e)
+            if args.diag:
+                self.trace.append((idx, round(e, 5), int(r["stats"].iterations), int(r["num_matches"]),
+                                   round(float(np.abs(ts[i]).max()), 3)))
 
     def run_steps(n_steps: int, start_frame_idx: int, mem_kind: int, base_ptr: int, ring: int, download: bool,
                   sweep=None, timed=False):
@@ -410,6 +415,9 @@ def main():
         out = dict(pairs=pairs + p2, rows=rows + r2, dev_ms=dev_ms, wall_s=wall, clocks=clocks, times=times,
                    launches=launches)
         if sweep is not None:
+            if args.diag and rank == 0:
+                import sys
+                print(json.dumps({"track_trace(idx, |t err|, LM iters, matches, |t|max)": sweep.trace[::16]}), file=sys.stderr)
             out["track"] = {"frames_tracked": sweep.tracked,
                             "matches_per_frame": sweep.matches / max(sweep.tracked, 1),
                             "lm_iterations_per_frame": sweep.iterations / max(sweep.tracked, 1),

@@ -28,6 +28,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--config", default="4k", choices=sorted(CONFIGS))
     ap.add_argument("--frames", type=int, default=64)
+    ap.add_argument("--no-refine", action="store_true")
     args = ap.parse_args()
     from oracle import synth          # input generator only
     from polychase_b200 import capi, polychase_core as core
@@ -81,11 +82,70 @@ def main():
     th.join()
     dt = time.perf_counter() - t0
     pairs = 8 * F - 30
-    print(json.dumps({"metric": "OpticalFlowThread (Analyze Video) wall clock at %s" % args.config, "frames": F,
+    out_lines = []
+    out_lines.append(json.dumps({"metric": "OpticalFlowThread (Analyze Video) wall clock at %s" % args.config, "frames": F,
                       "directed_pairs": pairs, "wall_s": dt, "frames_per_s": F / dt, "pairs_per_s": pairs / dt,
                       "db_bytes": os.path.getsize(dbp), "errors": errors,
                       "first_request_after_s": first_provide[0], "first_provide_s": first_provide[1],
                       "other_provides_total_s": provide_s}))
+
+    # ---- TrackerThread (Track Sequence, tracker.cc:194-213) over the same database ---------------
+    def pump(thread, on_msg):
+        while True:
+            m = thread.try_pop()
+            if m is None:
+                time.sleep(0.0002)
+                continue
+            if isinstance(m, bool):
+                return
+            on_msg(m)
+
+    verts, tris = synth.plane_mesh(w, h, scale)
+    mesh = core.AcceleratedMesh(verts, tris)
+    intr = core.CameraIntrinsics(K["fx"], K["fy"], K["cx"], K["cy"], 1.0, w, h, core.CameraConvention.OpenCV)
+    view = np.eye(4, dtype=np.float32)
+    view[:3, :3] = Rs[0]
+    view[:3, 3] = ts[0]
+    scene = core.SceneTransformations(np.eye(4, dtype=np.float32), view, intr)
+    bo = core.BundleOptions()
+    bo.loss_type = core.LossType.Cauchy
+    results = []
+    t0 = time.perf_counter()
+    tt = core.TrackerThread(dbp, 1, F, scene, mesh, False, False, bo)
+    pump(tt, lambda m: results.append(m) if isinstance(m, core.FrameTrackingResult) else errors.append(m.what()))
+    tt.join()
+    dt = time.perf_counter() - t0
+    t_err = max(float(np.abs(np.array(r.pose.t) - ts[r.frame - 1]).max()) for r in results) if results else None
+    out_lines.append(json.dumps({"metric": "TrackerThread (Track Sequence) wall clock at %s" % args.config,
+                                 "frames_tracked": len(results), "wall_s": dt, "frames_per_s": len(results) / dt,
+                                 "max_abs_translation_error": t_err, "errors": errors}))
+
+    # ---- RefinerThread (Refine Sequence, refiner.cc:692-725) --------------------------------------
+    if results and len(results) == F - 1 and not args.no_refine:
+        traj = core.CameraTrajectory(1, F)
+        for k in range(1, F + 1):
+            pz = core.Pose()
+            if k in (1, F):
+                cs = capi.camera_state(K, Rs[k - 1], ts[k - 1])
+                pz.q, pz.t = [float(v) for v in cs.q], [float(v) for v in cs.t]
+            else:
+                r = results[k - 2]
+                pz.q, pz.t = r.pose.q, r.pose.t
+            traj.set(k, core.CameraState(intr, pz))
+        updates = []
+        t0 = time.perf_counter()
+        rt = core.RefinerThread(dbp, traj, np.eye(4, dtype=np.float32), mesh, False, False, bo)
+        pump(rt, lambda m: updates.append(m) if isinstance(m, core.RefineTrajectoryUpdate) else errors.append(m.what()))
+        rt.join()
+        dt = time.perf_counter() - t0
+        out_lines.append(json.dumps({"metric": "RefinerThread (Refine Sequence) wall clock at %s" % args.config,
+                                     "frames": F, "wall_s": dt, "updates": len(updates),
+                                     "initial_cost": updates[-1].stats.initial_cost if updates else None,
+                                     "final_cost": updates[-1].stats.cost if updates else None,
+                                     "iterations": updates[-1].stats.iterations if updates else None,
+                                     "errors": errors}))
+    for l in out_lines:
+        print(l)
 
 
 if __name__ == "__main__":
