@@ -6,7 +6,12 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <condition_variable>
 #include <deque>
+#include <exception>
+#include <map>
+#include <mutex>
+#include <thread>
 
 namespace pch {
 
@@ -25,6 +30,97 @@ std::string Format(const char* fmt, ...) {
 void Check(pc_ctx* ctx, int rc) {
     if (rc != PC_OK) ThrowPcError(ctx, rc);
 }
+
+// Write-behind for the analyze pass: finished frames are copied out of the page-locked result slab
+// and written by this thread, one transaction per frame, while the caller already waits for the
+// next frame.  The connection is used by this thread only between Start() and Finish().
+class FlowWriter {
+   public:
+    struct Pair {
+        int32_t from, to;
+        std::vector<uint32_t> idx;
+        std::vector<float> tgt, err;
+    };
+    struct Item {
+        int32_t frame_id = 0;
+        std::vector<float> kps;        // x, y
+        std::vector<Pair> pairs;
+    };
+    explicit FlowWriter(Database& db) : db_(db) { thread_ = std::thread([this] { Run(); }); }
+    ~FlowWriter() {
+        try {
+            Finish();
+        } catch (...) {
+        }
+    }
+    // Rethrows what a previous write threw.  Blocks while kMaxQueued frames wait (back-pressure).
+    void Push(Item&& it) {
+        std::unique_lock<std::mutex> lk(mtx_);
+        space_.wait(lk, [&] { return queue_.size() < kMaxQueued || error_; });
+        if (error_) std::rethrow_exception(error_);
+        queue_.push_back(std::move(it));
+        work_.notify_one();
+    }
+    // Drains the queue, stops the thread, rethrows a write error.
+    void Finish() {
+        {
+            std::lock_guard<std::mutex> lk(mtx_);
+            done_ = true;
+        }
+        work_.notify_one();
+        if (thread_.joinable()) thread_.join();
+        if (error_) {
+            std::exception_ptr e = error_;
+            error_ = nullptr;
+            std::rethrow_exception(e);
+        }
+    }
+
+   private:
+    static constexpr size_t kMaxQueued = 8;
+    void Run() {
+        for (;;) {
+            Item it;
+            {
+                std::unique_lock<std::mutex> lk(mtx_);
+                work_.wait(lk, [&] { return !queue_.empty() || done_; });
+                if (queue_.empty()) return;
+                it = std::move(queue_.front());
+                queue_.pop_front();
+            }
+            space_.notify_one();
+            if (error_) continue;                          // after a failure: drop the rest
+            try {
+                db_.Begin();
+                try {
+                    if (!db_.KeypointsExist(it.frame_id))                          // ReadOrGenerateKeypoints :168-178
+                        db_.WriteKeypoints(it.frame_id, it.kps.data(), it.kps.size() / 2);
+                    for (const Pair& p : it.pairs) {
+                        if (db_.ImagePairFlowExists(p.from, p.to)) continue;       // :286
+                        // a pair row references the source frame's keypoints row (FOREIGN KEY): the source
+                        // is either this frame or an earlier one, both already written
+                        db_.WriteImagePairFlow(p.from, p.to, p.idx.data(), p.tgt.data(), p.err.data(), p.idx.size());
+                    }
+                } catch (...) {
+                    db_.Commit();
+                    throw;
+                }
+                db_.Commit();
+            } catch (...) {
+                std::lock_guard<std::mutex> lk(mtx_);
+                error_ = std::current_exception();
+                space_.notify_all();
+            }
+        }
+    }
+    Database& db_;
+    std::thread thread_;
+    std::mutex mtx_;
+    std::condition_variable work_, space_;
+    std::deque<Item> queue_;
+    std::exception_ptr error_;
+    bool done_ = false;
+};
 
 }  // namespace
 
@@ -48,9 +144,15 @@ void GenerateOpticalFlowDatabase(const VideoInfo& video_info, FrameAccessorFunct
     const int w = (int)video_info.width, h = (int)video_info.height;
     int max_features = detector_options.max_corners > 0 ? detector_options.max_corners
                                                         : std::max(16384, (int)(((int64_t)w * h) / 16));
-    // keypoints read back from an earlier run may be more numerous than max_corners
-    for (int32_t f = from; f < to; f++)
-        if (db.KeypointsExist(f)) max_features = std::max(max_features, (int)db.ReadKeypoints(f).size());
+    // Resume: keypoints already in the database are used as they are (they may be more numerous than
+    // max_corners).  They are read now, because once the write-behind thread runs the connection is its.
+    std::map<int32_t, Keypoints> stored_kps;
+    for (int32_t f = from; f < to; f++) {
+        if (!db.KeypointsExist(f)) continue;
+        Keypoints kps = db.ReadKeypoints(f);
+        max_features = std::max(max_features, (int)kps.size());
+        if (!kps.empty()) stored_kps.emplace(f, std::move(kps));
+    }
     auto dc = AcquireDeviceContext(w, h, max_features);
     pc_ctx* ctx = dc->ctx;
     std::lock_guard<std::mutex> lk(dc->mtx);
@@ -65,26 +167,24 @@ void GenerateOpticalFlowDatabase(const VideoInfo& video_info, FrameAccessorFunct
     } guard{ctx};
 
     std::deque<std::shared_ptr<void>> alive;     // frames stay alive until their upload was consumed
+    FlowWriter writer(db);
     auto drain_one = [&]() {
         pc_frame_result r;
         Check(ctx, pc_analyze_pop(ctx, &r, 1));
-        db.Begin();
-        try {
-            if (!db.KeypointsExist(r.frame_id))                           // ReadOrGenerateKeypoints :168-178
-                db.WriteKeypoints(r.frame_id, r.keypoints, (size_t)r.num_keypoints);
-            for (int k = 0; k < r.num_pairs; k++) {
-                const pc_pair_rows& p = r.pairs[k];
-                if (db.ImagePairFlowExists(p.image_id_from, p.image_id_to)) continue;     // :286
-                // a pair row references the source frame's keypoints row (FOREIGN KEY): the source is
-                // either this frame or an earlier one, both already written
-                db.WriteImagePairFlow(p.image_id_from, p.image_id_to, p.src_kps_indices, p.tgt_kps, p.flow_errors,
-                                      (size_t)p.rows);
-            }
-        } catch (...) {
-            db.Commit();
-            throw;
+        FlowWriter::Item it;
+        it.frame_id = r.frame_id;
+        it.kps.assign(r.keypoints, r.keypoints + 2 * (size_t)r.num_keypoints);
+        it.pairs.resize((size_t)r.num_pairs);
+        for (int k = 0; k < r.num_pairs; k++) {
+            const pc_pair_rows& p = r.pairs[k];
+            FlowWriter::Pair& q = it.pairs[(size_t)k];
+            q.from = p.image_id_from;
+            q.to = p.image_id_to;
+            q.idx.assign(p.src_kps_indices, p.src_kps_indices + p.rows);
+            q.tgt.assign(p.tgt_kps, p.tgt_kps + 2 * (size_t)p.rows);
+            q.err.assign(p.flow_errors, p.flow_errors + p.rows);
         }
-        db.Commit();
+        writer.Push(std::move(it));
         if (!alive.empty()) alive.pop_front();
     };
 
@@ -101,17 +201,16 @@ void GenerateOpticalFlowDatabase(const VideoInfo& video_info, FrameAccessorFunct
         if (!frame) throw std::runtime_error(Format("Rquested frame #%d was not provided", frame_id));   // :251-254
         PCH_CHECK((uint32_t)frame->height == video_info.height);          // :196-198
         PCH_CHECK((uint32_t)frame->width == video_info.width);
-        // resume: keypoints already in the database are used as they are
-        if (db.KeypointsExist(frame_id)) {
-            const Keypoints kps = db.ReadKeypoints(frame_id);
-            if (!kps.empty()) Check(ctx, pc_analyze_preset_keypoints(ctx, frame_id, kps[0].data(), (int)kps.size()));
-        }
+        const auto stored = stored_kps.find(frame_id);
+        if (stored != stored_kps.end())
+            Check(ctx, pc_analyze_preset_keypoints(ctx, frame_id, stored->second[0].data(), (int)stored->second.size()));
         if (pc_analyze_pending(ctx) >= 3) drain_one();
         Check(ctx, pc_analyze_push_frame(ctx, frame_id, frame->data, frame->stride,
                                          frame->pinned ? PC_MEM_HOST_PINNED : PC_MEM_HOST));
         alive.push_back(frame->keep_alive);
     }
     while (pc_analyze_pending(ctx) > 0) drain_one();
+    writer.Finish();                                                      // every row is in the database
     if (callback) callback(1.0, "Done");
 }
 
