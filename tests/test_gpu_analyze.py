@@ -183,3 +183,45 @@ def test_tiny_and_flat_frames(ctx_small, w, h):
     ctx_small.upload_gray(42, g)
     idx, tgt, err = ctx_small.lk_pair(41, 42)
     assert len(idx) == 0 and len(tgt) == 0 and len(err) == 0
+
+
+def test_streaming_with_a_featureless_frame_and_short_clips(ctx_small):
+    """Ragged input: a flat frame in the middle of a clip (no keypoints: its outgoing pairs have zero rows,
+    its incoming pairs are tracked into a constant image), and clips shorter than the +-8 window."""
+    from polychase_b200 import capi
+    w, h, F = 320, 240, 5
+    clip = synth.Clip(w, h, F, seed=33, first_frame=0)
+    frames = {k: clip.rgb(k) for k in range(F)}
+    frames[2] = np.full((h, w, 3), 90, np.uint8)
+    go = capi.default_gftt(max_corners=250)
+    ctx_small.analyze_begin(w, h, 0, F, go)
+    kps, pairs = {}, {}
+    for k in range(F):
+        ctx_small.analyze_push(k, frames[k])
+    while ctx_small.analyze_pending():
+        r = ctx_small.analyze_pop()
+        kps[r["frame_id"]] = np.array(r["keypoints"]).copy()
+        for (a, b, rows, idx, tgt, err) in r["pairs"]:
+            pairs[(a, b)] = (np.array(idx).copy(), np.array(tgt).copy(), np.array(err).copy())
+    ctx_small.analyze_end()
+    expect = sorted((a, a + d) for a in range(F) for d in (-8, -4, -2, -1, 1, 2, 4, 8) if 0 <= a + d < F)
+    assert sorted(pairs) == expect
+    assert kps[2].shape == (0, 2)
+    grays = {k: restate.rgb2gray(frames[k]) for k in frames}
+    pyr = {k: restate.pyramid(grays[k], 3) for k in frames}
+    for (a, b) in expect:
+        idx, tgt, err = pairs[(a, b)]
+        if a == 2:
+            assert len(idx) == 0
+            continue
+        wn, ws, we = restate.lk(pyr[a], pyr[b], kps[a])
+        ok = ws == 1
+        assert np.array_equal(idx, np.nonzero(ok)[0].astype(np.uint32)), (a, b)
+        assert np.array_equal(_u32(tgt), _u32(wn[ok])), (a, b)
+        assert np.array_equal(_u32(err), _u32(we[ok])), (a, b)
+    # a one-frame "clip": keypoints, no pairs
+    ctx_small.analyze_begin(w, h, 7, 1, go)
+    ctx_small.analyze_push(7, frames[0])
+    r = ctx_small.analyze_pop()
+    ctx_small.analyze_end()
+    assert r["frame_id"] == 7 and len(r["pairs"]) == 0 and len(r["keypoints"]) == len(kps[0])
