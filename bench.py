@@ -259,7 +259,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from oracle import synth   # input generator only (texture + camera path); not the checker here
+    from polychase_b200 import synth   # input generator (texture + camera path)
     from polychase_b200 import capi
 
     torch.cuda.set_device(local_rank)

@@ -33,7 +33,7 @@ def main():
     ap.add_argument("--reps", type=int, default=5, help="timed repetitions of the cost / build entry points")
     args = ap.parse_args()
 
-    from oracle import synth          # input generator only
+    from polychase_b200 import synth  # input generator
     from polychase_b200 import capi
     from polychase_b200.geometry import quat_from_matrix
 

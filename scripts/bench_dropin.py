@@ -30,7 +30,7 @@ def main():
     ap.add_argument("--frames", type=int, default=64)
     ap.add_argument("--no-refine", action="store_true")
     args = ap.parse_args()
-    from oracle import synth          # input generator only
+    from polychase_b200 import synth  # input generator
     from polychase_b200 import capi, polychase_core as core
 
     w, h, max_corners = CONFIGS[args.config]
