@@ -109,7 +109,7 @@ min_eig_kernel(const uint8_t* __restrict__ gray, int w, int h, int pitch, float*
 
     uint32_t word = live ? load_gray(gray, w, h, pitch, xb, y0 - 2, fast) : 0u;
     const int steps = (y_end - y0) + 4;
-#pragma unroll 1
+#pragma unroll 3
     for (int k = 0; k < steps; k++) {
         // prefetch the next gray row while this one is processed
         uint32_t next_word = 0u;

@@ -16,7 +16,7 @@ if [ -n "$KERNELS" ] && [ "$KERNELS" != "none" ]; then
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file $OUT/${TAG}_launches.csv \
     python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu-baseline > $OUT/${TAG}_ncu_b.log 2>&1
 # one full capture of the named kernels (skip the warm-up launches)
-timeout 900 ncu --set full --clock-control none --import-source on -k "regex:$KERNELS" -s 40 -c 8 \
+timeout 900 ncu --set full --clock-control none --import-source on -k "regex:$KERNELS" -s ${NCU_SKIP:-40} -c ${NCU_COUNT:-8} \
     -o $OUT/${TAG}_prof -f python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu-baseline > $OUT/${TAG}_ncu_full.log 2>&1
 fi
 ls -la $OUT | tail -8
