@@ -22,8 +22,10 @@
 // and marches down it.  Each lane holds NC adjacent columns (one aligned gray load per row, one
 // aligned eig vector store per row); the +-1 column neighbours come from the adjacent lanes by
 // shuffle, the +-1 row neighbours are rolling registers.  Lanes 0 and 31 only feed their
-// neighbours (the halo columns of the tile).  NC = 2 keeps the rolling state (24 floats + 12
-// doubles per lane) small enough for 24 resident warps per SM.
+// neighbours (the halo columns of the tile).  NC = 4 with the march loop unrolled by 3 (the rolling
+// windows rotate through registers instead of being moved) measures 63 us at 4K against 76 us for
+// NC = 2 rolled: the halo shuffles and conversions are shared by twice the columns, which outweighs
+// the drop to 16 resident warps per SM.
 //
 // Rows outside the image: the march simply continues over the REFLECT_101 row indices.  For
 // the one row each side that the box filter needs (cov row -1 := cov row 1, cov row h := cov
@@ -37,7 +39,7 @@
 
 namespace pc {
 
-constexpr int ME_NC = 2;                       // columns per lane
+constexpr int ME_NC = 4;                       // columns per lane
 constexpr int ME_COLS = 30 * ME_NC;            // output columns per warp tile (lanes 1..30)
 constexpr int ME_ROWS = 32;                    // output rows per warp tile
 constexpr int ME_WARPS = 4;
