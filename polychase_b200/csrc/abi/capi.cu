@@ -97,6 +97,7 @@ static FrameSlot* acquire_slot(pc_ctx* c, int32_t frame_id) {
     s->frame_id = frame_id;
     s->stamp = ++c->stamp;
     s->has_kps = false;
+    s->has_tmpl = false;
     s->n_kps_host = -1;
     return s;
 }
@@ -186,10 +187,13 @@ static LKParams make_lk_params(const pc_flow_opts* fo) {
     return p;
 }
 
-static void fill_pair(pc_ctx* c, LKPair& p, const FrameSlot& a, const FrameSlot& b, int k, const PairOut& out) {
+static void fill_pair(pc_ctx* c, LKPair& p, const FrameSlot& a, const FrameSlot& b, int k, const PairOut& out,
+                      bool use_templates = false) {
     const int cap = c->lim.max_features;
     p.a = view_of(a);
     p.b = view_of(b);
+    p.tmpl = LKTemplates{nullptr, nullptr, 0};
+    if (use_templates && a.has_tmpl) p.tmpl = LKTemplates{a.tmpl, a.tmpl_sums, cap};
     p.pts = a.kps;
     p.n_pts = a.n_kps;
     p.next = c->lk_next + (size_t)k * cap * 2;
@@ -270,6 +274,8 @@ pc_ctx::~pc_ctx() {
     if (side) cudaStreamSynchronize(side);
     if (track && track->stream) cudaStreamSynchronize(track->stream);
     for (auto& s : slots) {
+        cudaFree(s.tmpl);
+        cudaFree(s.tmpl_sums);
         cudaFree(s.base);
         cudaFree(s.kps); cudaFree(s.n_kps);
     }
@@ -708,7 +714,28 @@ int pc_analyze_begin(pc_ctx* c, const pc_video_info* vi, const pc_gftt_opts* go,
         }
     }
     if (c->side) PC_CUDA(c, cudaStreamSynchronize(c->side));
-    for (auto& s : c->slots) s.used = false;
+    for (auto& s : c->slots) { s.used = false; s.has_tmpl = false; }
+    // template cache of the 10x10 LK kernel: (max_level + 1) x max_features x 640 B per slot, kept as
+    // long as it stays under 4 GB for the whole ring (the kernel computes templates itself otherwise)
+    {
+        const int tl = std::min(std::max(fo->max_level, 0) + 1, kMaxLevels);
+        const size_t per_slot = (size_t)tl * c->lim.max_features * kLkTemplateBytesPerPoint;
+        const bool want = fo->window_size == 10 && per_slot * c->slots.size() <= ((size_t)4 << 30) && !getenv("PC_NO_LK_TEMPLATES");
+        for (auto& s : c->slots) {
+            if (want && s.tmpl && s.tmpl_levels >= tl) continue;
+            cudaFree(s.tmpl); cudaFree(s.tmpl_sums);
+            s.tmpl = nullptr; s.tmpl_sums = nullptr; s.tmpl_levels = 0;
+            if (!want) continue;
+            if (cudaMalloc(&s.tmpl, per_slot) != cudaSuccess ||
+                cudaMalloc(&s.tmpl_sums, (size_t)tl * c->lim.max_features * 4 * sizeof(float)) != cudaSuccess) {
+                cudaGetLastError();
+                cudaFree(s.tmpl); cudaFree(s.tmpl_sums);
+                s.tmpl = nullptr; s.tmpl_sums = nullptr;
+                continue;
+            }
+            s.tmpl_levels = tl;
+        }
+    }
     c->download_hint = false;
     c->inflight.clear();
     c->next_stage = 0;
@@ -787,6 +814,17 @@ static int enqueue_lk(pc_ctx* c, Stage& st, FrameSlot* f) {
         PC_CUDA(c, cudaStreamWaitEvent(c->side, st.detected, 0));
         lks = c->side;
     }
+    const LKParams lkp = make_lk_params(&c->fopts);
+    int rc;
+    // source templates of this frame's keypoints (once per frame; its eight pairs load them)
+    if (f->tmpl && lkp.win == 10 && lkp.max_level + 1 <= f->tmpl_levels) {
+        span_begin(c, KF_LK, lks);
+        launch_lk10_templates(view_of(*f), f->kps, f->n_kps, c->lim.max_features, lkp, f->tmpl, f->tmpl_sums, lks);
+        span_end(c, lks);
+        rc = check_launch(c, "lk templates", 1);
+        if (rc) return rc;
+        f->has_tmpl = true;
+    }
     LKBatch batch{};
     batch.cap = c->lim.max_features;
     if (c->gopts.max_corners > 0) batch.cap = std::min(batch.cap, c->gopts.max_corners);
@@ -798,10 +836,10 @@ static int enqueue_lk(pc_ctx* c, Stage& st, FrameSlot* f) {
         FrameSlot* o = find_slot(c, other);
         if (!o) return fail(c, PC_ERR_STATE, "frame " + std::to_string(other) + " fell out of the ring");
         st.from[np] = other; st.to[np] = frame_id;
-        fill_pair(c, batch.pair[np], *o, *f, np, st.dev[np]);
+        fill_pair(c, batch.pair[np], *o, *f, np, st.dev[np], true);
         np++;
         st.from[np] = frame_id; st.to[np] = other;
-        fill_pair(c, batch.pair[np], *f, *o, np, st.dev[np]);
+        fill_pair(c, batch.pair[np], *f, *o, np, st.dev[np], true);
         np++;
     }
     // presets may exceed max_corners
@@ -811,9 +849,8 @@ static int enqueue_lk(pc_ctx* c, Stage& st, FrameSlot* f) {
     }
     batch.num_pairs = np;
     st.num_pairs = np;
-    int rc;
     if (np > 0) {
-        const LKParams p = make_lk_params(&c->fopts);
+        const LKParams& p = lkp;
         span_begin(c, KF_LK, lks);
         launch_lk(batch, p, lks);
         span_end(c, lks);

@@ -28,6 +28,11 @@ struct FrameSlot {
     int* greedy_remaining = nullptr;
     int n_kps_host = -1;          // -1 = not known on host yet
     bool has_kps = false;
+    // streaming analyzer, 10x10 window: the LK source templates of this frame's keypoints (lk10.cu)
+    uint4* tmpl = nullptr;
+    float* tmpl_sums = nullptr;
+    int tmpl_levels = 0;          // levels the allocation holds
+    bool has_tmpl = false;        // computed for the frame and keypoints the slot holds now
 };
 
 enum KernelFamily { KF_GRAY_PYR = 0, KF_MIN_EIG, KF_SELECT, KF_LK, KF_COMPACT, KF_RAYCAST, KF_PNP, KF_BA, KF_COUNT };

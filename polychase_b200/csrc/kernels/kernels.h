@@ -83,8 +83,18 @@ struct LKParams {
     double eps;          // already clamped; squared inside
     double min_eig;
 };
+// Source templates of one frame's keypoints, precomputed once per frame for the 10x10 kernel
+// (lk10.cu): per (level, keypoint) the five lanes' 20 pixels of Ival / Ix / Iy packed in 32 words per
+// lane, and A11, A12, A22.  words == nullptr: the LK kernel computes the templates itself.
+struct LKTemplates {
+    const uint4* words;          // [level][cap][5 lanes][8 uint4]
+    const float* sums;           // [level][cap][4]
+    int cap;
+};
+constexpr size_t kLkTemplateBytesPerPoint = 5 * 8 * 16;     // per level
 struct LKPair {
     PyramidView a, b;            // source / target frame
+    LKTemplates tmpl;
     const float* pts;            // source keypoints (x,y)
     const int* n_pts;            // device count
     float* next;                 // dense outputs, capacity `cap`
@@ -101,6 +111,9 @@ struct LKBatch {
 };
 void launch_lk(const LKBatch& batch, const LKParams& p, cudaStream_t s);
 void launch_lk_compact(const LKBatch& batch, cudaStream_t s);
+// Templates of frame `a`'s keypoints for every level the 10x10 kernel will visit (win must be 10).
+void launch_lk10_templates(const PyramidView& a, const float* pts, const int* n_pts, int cap, const LKParams& p,
+                           uint4* words, float* sums, cudaStream_t s);
 
 // ---- synthetic frame warp (synth.cu) ------------------------------------------------
 void launch_synth_warp(const uint8_t* tex, int w, int h, int tex_pitch, const double Hinv[9],

@@ -25,6 +25,8 @@
 //     warp takes only when one of its keypoints' patches leaves the image at that level.
 // Integer stages are exact and float stages use explicit-rounding intrinsics (file is compiled
 // with -fmad=false), so results are bit-identical to the oracle (tests/test_gpu_analyze.py).
+#include <algorithm>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -226,6 +228,69 @@ __device__ __forceinline__ void window_pass(const LevelRef& B, int inx, int iny,
     }
 }
 
+// ---- template cache ---------------------------------------------------------------------------
+// A frame's keypoints are the source of up to eight pairs (four in the batch of its own frame, one in
+// each of the batches of frames +1, +2, +4, +8), and the template of a (keypoint, level) -- the
+// lane's 20 pixels of Ival / Ix / Iy and the three structure-tensor sums -- depends on the source
+// frame only.  lk10_template_kernel computes them once per frame; the LK kernel then loads a lane's
+// 32 packed words (8 x 16 bytes, the pentad's five lanes read five consecutive 128-byte lines)
+// instead of re-running the 13-row template pass (~1200 instructions) for every pair.
+//   words 0..9 : Ival[2k] | Ival[2k+1] << 16   (0 <= Ival <= 8160)
+//   words 10..29: (Ix[i] & 0xffff) | Iy[i] << 16 (|Ix|, |Iy| <= 4080)
+__global__ void __launch_bounds__(LK_WARPS * 32, 4) lk10_template_kernel(PyramidView a, const float* __restrict__ pts,
+                                                                         const int* __restrict__ n_pts, int cap, int nlev,
+                                                                         uint4* __restrict__ words,
+                                                                         float* __restrict__ sums) {
+    const int level = blockIdx.y;
+    if (level >= min(a.levels, nlev)) return;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int grp = lane / PENTAD, role = lane - grp * PENTAD;
+    const int base = grp < PTS_PER_WARP ? grp * PENTAD : 0;
+    const int npts = min(*n_pts, cap);
+    const int pi = (blockIdx.x * LK_WARPS + wib) * PTS_PER_WARP + grp;
+    const bool valid = grp < PTS_PER_WARP && pi < npts;
+    if (!__any_sync(FULL, valid)) return;
+    const int simd_flag = role < 4 ? 1 : 0;
+    const int xa = simd_flag ? role : 8;
+    float ptx = 0.f, pty = 0.f;
+    if (valid) { ptx = pts[2 * pi]; pty = pts[2 * pi + 1]; }
+    const float halfw = (WIN - 1) * 0.5f;
+    const float FLT_SCALE = 1.f / (float)(1 << 20);
+    const LevelRef A = {a.data[level], a.w[level], a.h[level], a.pitch[level]};
+    const float scale = 1.f / (float)(1 << level);
+    const float prevx = __fsub_rn(__fmul_rn(ptx, scale), halfw), prevy = __fsub_rn(__fmul_rn(pty, scale), halfw);
+    const int ipx = __float2int_rd(prevx), ipy = __float2int_rd(prevy);
+    const bool act = valid && !(ipx < -WIN || ipx >= A.w || ipy < -WIN || ipy >= A.h);
+    int w00, w01, w10, w11;
+    bilinear_weights(__fsub_rn(prevx, (float)ipx), __fsub_rn(prevy, (float)ipy), w00, w01, w10, w11);
+    int Ival[20], Ix[20], Iy[20];
+    float a11 = 0.f, a12 = 0.f, a22 = 0.f;
+    const bool t_inside = ipx >= 1 && ipy >= 1 && ipx + WIN + 1 < A.w && ipy + WIN + 1 < A.h;
+    const bool any_border = __any_sync(FULL, act && !t_inside);
+    if (act) {
+        if (any_border) template_pass<true>(A, ipx, ipy, xa, simd_flag, w00, w01, w10, w11, Ival, Ix, Iy, a11, a12, a22);
+        else template_pass<false>(A, ipx, ipy, xa, simd_flag, w00, w01, w10, w11, Ival, Ix, Iy, a11, a12, a22);
+    }
+    __syncwarp();
+    const float A11 = __fmul_rn(pentad_total(a11, base, role), FLT_SCALE);
+    const float A12 = __fmul_rn(pentad_total(a12, base, role), FLT_SCALE);
+    const float A22 = __fmul_rn(pentad_total(a22, base, role), FLT_SCALE);
+    if (!act) return;
+    uint32_t wv[32];
+#pragma unroll
+    for (int k = 0; k < 10; k++) wv[k] = (uint32_t)Ival[2 * k] | ((uint32_t)Ival[2 * k + 1] << 16);
+#pragma unroll
+    for (int i = 0; i < 20; i++) wv[10 + i] = ((uint32_t)Ix[i] & 0xffffu) | ((uint32_t)Iy[i] << 16);
+    wv[30] = 0u; wv[31] = 0u;
+    uint4* dst = words + (((size_t)level * cap + pi) * PENTAD + role) * 8;
+#pragma unroll
+    for (int q = 0; q < 8; q++) dst[q] = make_uint4(wv[4 * q], wv[4 * q + 1], wv[4 * q + 2], wv[4 * q + 3]);
+    if (role == 0) {
+        float* sp = sums + ((size_t)level * cap + pi) * 4;
+        *reinterpret_cast<float4*>(sp) = make_float4(A11, A12, A22, 0.f);
+    }
+}
+
 __global__ void __launch_bounds__(LK_WARPS * 32, 4) lk10_kernel(LKBatch batch, LKParams prm) {
     // large skips take several times more iterations (slow pairs are appended last): schedule
     // them first so the launch does not end on a tail of long blocks
@@ -270,9 +335,28 @@ __global__ void __launch_bounds__(LK_WARPS * 32, 4) lk10_kernel(LKBatch batch, L
         int w00, w01, w10, w11;
         bilinear_weights(__fsub_rn(prevx, (float)ipx), __fsub_rn(prevy, (float)ipy), w00, w01, w10, w11);
 
-        // ---- template ------------------------------------------------------------------------
-        float a11 = 0.f, a12 = 0.f, a22 = 0.f;
-        {
+        // ---- template: loaded from the frame's cache, or computed here ---------------------------
+        float A11, A12, A22;
+        if (pr.tmpl.words != nullptr) {                              // uniform per pair
+            A11 = 0.f; A12 = 0.f; A22 = 0.f;
+            if (act) {
+                const size_t slot = (size_t)level * pr.tmpl.cap + pi;
+                const uint4* q = pr.tmpl.words + (slot * PENTAD + role) * 8;
+                uint32_t wv[32];
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    const uint4 v = __ldg(q + k);
+                    wv[4 * k] = v.x; wv[4 * k + 1] = v.y; wv[4 * k + 2] = v.z; wv[4 * k + 3] = v.w;
+                }
+                const float4 sv = __ldg(reinterpret_cast<const float4*>(pr.tmpl.sums + slot * 4));
+                A11 = sv.x; A12 = sv.y; A22 = sv.z;
+#pragma unroll
+                for (int k = 0; k < 10; k++) { Ival[2 * k] = (int)(wv[k] & 0xffffu); Ival[2 * k + 1] = (int)(wv[k] >> 16); }
+#pragma unroll
+                for (int i = 0; i < 20; i++) { Ix[i] = (int)(short)(wv[10 + i] & 0xffffu); Iy[i] = (int)wv[10 + i] >> 16; }
+            }
+        } else {
+            float a11 = 0.f, a12 = 0.f, a22 = 0.f;
             // the 13x13 source patch [ipx-1, ipx+11] x [ipy-1, ipy+11] lies inside the level
             const bool t_inside = ipx >= 1 && ipy >= 1 && ipx + WIN + 1 < A.w && ipy + WIN + 1 < A.h;
             const bool any_border = __any_sync(FULL, act && !t_inside);
@@ -281,10 +365,10 @@ __global__ void __launch_bounds__(LK_WARPS * 32, 4) lk10_kernel(LKBatch batch, L
                 else template_pass<false>(A, ipx, ipy, xa, simd_flag, w00, w01, w10, w11, Ival, Ix, Iy, a11, a12, a22);
             }
             __syncwarp();
+            A11 = __fmul_rn(pentad_total(a11, base, role), FLT_SCALE);
+            A12 = __fmul_rn(pentad_total(a12, base, role), FLT_SCALE);
+            A22 = __fmul_rn(pentad_total(a22, base, role), FLT_SCALE);
         }
-        const float A11 = __fmul_rn(pentad_total(a11, base, role), FLT_SCALE);
-        const float A12 = __fmul_rn(pentad_total(a12, base, role), FLT_SCALE);
-        const float A22 = __fmul_rn(pentad_total(a22, base, role), FLT_SCALE);
         float D = __fsub_rn(__fmul_rn(A11, A22), __fmul_rn(A12, A12));
         const float dA = __fsub_rn(A11, A22);
         const float rad = __fadd_rn(__fmul_rn(dA, dA), __fmul_rn(__fmul_rn(4.f, A12), A12));
@@ -365,6 +449,14 @@ __global__ void __launch_bounds__(LK_WARPS * 32, 4) lk10_kernel(LKBatch batch, L
 }
 
 }  // namespace
+
+void launch_lk10_templates(const PyramidView& a, const float* pts, const int* n_pts, int cap, const LKParams& p,
+                           uint4* words, float* sums, cudaStream_t s) {
+    const int per_block = LK_WARPS * PTS_PER_WARP;
+    const int nlev = std::min(a.levels, p.max_level + 1);
+    dim3 grid((cap + per_block - 1) / per_block, nlev);
+    lk10_template_kernel<<<grid, LK_WARPS * 32, 0, s>>>(a, pts, n_pts, cap, p.max_level + 1, words, sums);
+}
 
 void launch_lk10(const LKBatch& batch, const LKParams& p, cudaStream_t s) {
     const int per_block = LK_WARPS * PTS_PER_WARP;
