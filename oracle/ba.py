@@ -1,5 +1,8 @@
 """float32 restatement of the reference's trajectory refiner -- TEST INFRASTRUCTURE.
 
+PARITY UNPINNED: no reference test or golden vector exists for the refiner and it cannot be compiled here
+(Eigen, Embree absent); checked by Jacobian finite differences and ground-truth recovery only.
+
   RefinementProblemBase::Evaluate / EvaluateWithJacobian   /root/reference/cpp/refiner.cc:274-506
   GlobalRefinementProblem (edges, weights, Step)            /root/reference/cpp/refiner.cc:250-257,578-647
   LevMarqSparseSolver (normal equations, cost, LM loop)     /root/reference/cpp/pnp/lev_marq.h:391-871

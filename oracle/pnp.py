@@ -1,5 +1,9 @@
 """float32 restatement of the reference's per-frame pose solve -- TEST INFRASTRUCTURE.
 
+PARITY UNPINNED: the reference ships no test or golden vector for this path and cannot be compiled
+here (Eigen is absent); checked only by analytic-vs-numeric Jacobians, the one known-answer LLT example of
+cpp/examples/levmarq_ill_conditioned_float32_issue.cpp and ground-truth recovery (tests/test_oracle_solvers.py).
+
   robust losses        /root/reference/cpp/pnp/robust_loss.h:47-104
   PnPProblem           /root/reference/cpp/pnp/pnp_problem.h:13-142
   LevMarqDenseSolver   /root/reference/cpp/pnp/lev_marq.h:99-389 (state machine: SURVEY App. B)

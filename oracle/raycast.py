@@ -1,5 +1,7 @@
 """Brute-force nearest-hit ray casting -- TEST INFRASTRUCTURE.
 
+PARITY UNPINNED against Embree itself (absent); exact against the analytic plane / brute force.
+
 Stands in for Embree's rtcIntersect1 (third party, Embree 4.3.1, not in /root/reference) as
 AcceleratedMesh::RayCast uses it (/root/reference/cpp/ray_casting.cc:65-121): nearest hit
 with tnear = 0, a hit on a masked triangle is a miss (it does not continue behind it,

@@ -1,5 +1,7 @@
 """float32 restatement of the reference's sequential tracker -- TEST INFRASTRUCTURE.
 
+PARITY UNPINNED beyond oracle/pnp.py's own checks (no reference fixtures for the tracker).
+
   SolveFrame              /root/reference/cpp/tracker.cc:36-131
   TrackCameraTrajectory   /root/reference/cpp/tracker.cc:133-192
   TrackSequence           /root/reference/cpp/tracker.cc:194-213
