@@ -577,7 +577,7 @@ void launch_select(const unsigned long long* cand, const int* cand_count, int ca
         // the short list lives in the (otherwise unused on this path) sort output buffer
         compact_top_kernel<<<sm_count, 256, 0, s>>>(ws.accepted, ws.accepted_count, ws.kept_hist, max_corners, kps_cap,
                                                     ws.sorted, ws.sel, kps_count, ws.bin_cursor, ws.bin_start);
-        select_rank_emit_kernel<<<sm_count * 4, 256, 0, s>>>(ws.sorted, ws.sel, kps_count, ws.kept_hist, ws.bin_start, w,
+        select_rank_emit_kernel<<<sm_count * 8, 256, 0, s>>>(ws.sorted, ws.sel, kps_count, ws.kept_hist, ws.bin_start, w,
                                                              kps_out);
     } else {
         size_t temp = ws.cub_temp_bytes;
