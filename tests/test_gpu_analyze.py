@@ -225,3 +225,54 @@ def test_streaming_with_a_featureless_frame_and_short_clips(ctx_small):
     r = ctx_small.analyze_pop()
     ctx_small.analyze_end()
     assert r["frame_id"] == 7 and len(r["pairs"]) == 0 and len(r["keypoints"]) == len(kps[0])
+
+
+def test_streaming_with_preset_keypoints_on_the_borders(ctx_small):
+    """Keypoints handed in (ReadOrGenerateKeypoints, opticalflow.cc:168-178) that sit on, near and outside
+    the image borders, at an odd frame size: the cached-template LK path must agree with the oracle bit
+    for bit (masked derivative taps, windows hanging over the edge, points outside a level)."""
+    from polychase_b200 import capi
+    w, h, F = 333, 251, 10
+    clip = synth.Clip(w, h, F, seed=41, first_frame=0)
+    frames = {k: clip.rgb(k) for k in range(F)}
+    rng = np.random.default_rng(7)
+    presets = {}
+    for k in range(F):
+        inside = np.stack([rng.uniform(0, w - 1, 300), rng.uniform(0, h - 1, 300)], 1)
+        edge = np.concatenate([
+            np.stack([rng.uniform(-6, 6, 60), rng.uniform(-6, h + 6, 60)], 1),
+            np.stack([rng.uniform(w - 7, w + 6, 60), rng.uniform(-6, h + 6, 60)], 1),
+            np.stack([rng.uniform(-6, w + 6, 60), rng.uniform(-6, 6, 60)], 1),
+            np.stack([rng.uniform(-6, w + 6, 60), rng.uniform(h - 7, h + 6, 60)], 1),
+            np.array([[0.0, 0.0], [w - 1.0, h - 1.0], [-30.0, 40.0], [w + 25.0, h + 25.0], [4.5, 4.5], [w - 5.5, h - 5.5]]),
+        ])
+        presets[k] = np.concatenate([inside, edge]).astype(np.float32)
+    ctx_small.analyze_begin(w, h, 0, F, capi.default_gftt(max_corners=100))
+    for k in range(F):
+        ctx_small.analyze_preset_keypoints(k, presets[k])
+    kps, pairs = {}, {}
+
+    def take(r):
+        kps[r["frame_id"]] = np.array(r["keypoints"]).copy()
+        for (a, b, rows, idx, tgt, err) in r["pairs"]:
+            pairs[(a, b)] = (np.array(idx).copy(), np.array(tgt).copy(), np.array(err).copy())
+
+    for k in range(F):
+        ctx_small.analyze_push(k, frames[k])
+        if ctx_small.analyze_pending() >= 4:
+            take(ctx_small.analyze_pop())
+    while ctx_small.analyze_pending():
+        take(ctx_small.analyze_pop())
+    ctx_small.analyze_end()
+    grays = {k: restate.rgb2gray(frames[k]) for k in frames}
+    nlev = ogftt.num_pyramid_levels(w, h, 10, 3)
+    pyr = {k: restate.pyramid(grays[k], 3)[:nlev] for k in frames}
+    assert len(pairs) == 8 * F - 30
+    for k in range(F):
+        assert np.array_equal(kps[k], presets[k])
+    for (a, b), (idx, tgt, err) in pairs.items():
+        wn, ws, we = restate.lk(pyr[a], pyr[b], presets[a])
+        ok = ws == 1
+        assert np.array_equal(idx, np.nonzero(ok)[0].astype(np.uint32)), (a, b)
+        assert np.array_equal(_u32(tgt), _u32(wn[ok])), (a, b)
+        assert np.array_equal(_u32(err), _u32(we[ok])), (a, b)
