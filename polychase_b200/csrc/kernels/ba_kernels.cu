@@ -433,37 +433,52 @@ __global__ void __launch_bounds__(1024) ba_solve_kernel(BAView v, float lambda) 
     }
     if (tid == 0) s_ok = 1;
     __syncthreads();
+    // Working set of one elimination step in shared memory: the diagonal block and the panel rows.
+    // Every global access of a phase is then one batch of independent loads (one L2 round trip per
+    // phase) instead of a chain of dependent ones inside a single thread.
+    __shared__ float Ds[9 * 9];                               // diagonal block (p <= 9)
+    __shared__ float Xs[(kBandBlocks - 1) * 9][9];            // panel rows X = B L_kk^-T
     for (int kf = 0; kf < nf; kf++) {
         float* D = L + ((size_t)kf * kBandBlocks) * pp;          // diagonal block of column kf
+        if (tid < pp) Ds[tid] = D[tid];
+        const int ilast = min(kf + kBandBlocks - 1, nf - 1);
+        const int nrows = (ilast - kf) * p;
+        float brow[9];
+        if (tid < nrows) {                                        // this thread's panel row, fetched meanwhile
+            const int i = kf + 1 + tid / p, a = tid % p;
+            const float* B = L + ((size_t)i * kBandBlocks + (i - kf)) * pp + a * p;
+            for (int c = 0; c < p; c++) brow[c] = B[c];
+        }
+        __syncthreads();
         if (tid == 0) {                                           // unblocked LLT of the p x p block
             for (int c = 0; c < p && s_ok; c++) {
-                float x = D[c * p + c];
-                for (int j = 0; j < c; j++) x -= D[c * p + j] * D[c * p + j];
+                float x = Ds[c * p + c];
+                for (int j = 0; j < c; j++) x -= Ds[c * p + j] * Ds[c * p + j];
                 if (!(x > 0.f)) { s_ok = 0; break; }
                 x = sqrtf(x);
-                D[c * p + c] = x;
+                Ds[c * p + c] = x;
                 for (int r = c + 1; r < p; r++) {
-                    float s = D[r * p + c];
-                    for (int j = 0; j < c; j++) s -= D[r * p + j] * D[c * p + j];
-                    D[r * p + c] = s / x;
+                    float s = Ds[r * p + c];
+                    for (int j = 0; j < c; j++) s -= Ds[r * p + j] * Ds[c * p + j];
+                    Ds[r * p + c] = s / x;
                 }
             }
             for (int r = 0; r < p; r++)
-                for (int c = r + 1; c < p; c++) D[r * p + c] = 0.f;
+                for (int c = r + 1; c < p; c++) Ds[r * p + c] = 0.f;
         }
         __syncthreads();
         if (!s_ok) break;
-        const int ilast = min(kf + kBandBlocks - 1, nf - 1);
+        if (tid < pp) D[tid] = Ds[tid];
         // panel: X = B * L_kk^-T for every block (i, kf), i in (kf, ilast]; one thread per row
-        const int nrows = (ilast - kf) * p;
         if (tid < nrows) {
             const int i = kf + 1 + tid / p, a = tid % p;
             float* B = L + ((size_t)i * kBandBlocks + (i - kf)) * pp + a * p;
             for (int c = 0; c < p; c++) {
-                float s = B[c];
-                for (int j = 0; j < c; j++) s -= B[j] * D[c * p + j];
-                B[c] = s / D[c * p + c];
+                float s = brow[c];
+                for (int j = 0; j < c; j++) s -= brow[j] * Ds[c * p + j];
+                brow[c] = s / Ds[c * p + c];
             }
+            for (int c = 0; c < p; c++) { B[c] = brow[c]; Xs[tid][c] = brow[c]; }
         }
         __syncthreads();
         // trailing update: block (i, j) -= X_i X_j^T for kf < j <= i <= ilast
@@ -475,8 +490,8 @@ __global__ void __launch_bounds__(1024) ba_solve_kernel(BAView v, float lambda) 
             while (acc + ii + 1 <= pr) { acc += ii + 1; ii++; }   // pr -> (ii, jj), jj <= ii
             const int jj = pr - acc;
             const int i = kf + 1 + ii, j = kf + 1 + jj;
-            const float* Xi = L + ((size_t)i * kBandBlocks + (i - kf)) * pp + a * p;
-            const float* Xj = L + ((size_t)j * kBandBlocks + (j - kf)) * pp + b * p;
+            const float* Xi = Xs[ii * p + a];
+            const float* Xj = Xs[jj * p + b];
             float s = 0.f;
             for (int q = 0; q < p; q++) s += Xi[q] * Xj[q];
             L[((size_t)i * kBandBlocks + (i - j)) * pp + a * p + b] -= s;
@@ -485,48 +500,62 @@ __global__ void __launch_bounds__(1024) ba_solve_kernel(BAView v, float lambda) 
     }
     if (tid == 0) v.scalars[4] = s_ok ? 1.f : 0.f;
     if (!s_ok) return;
-    // forward: y_i = L_ii^-1 (b_i - sum_{k=1..8} L_(i,i-k) y_(i-k))
+    // forward: y_i = L_ii^-1 (b_i - sum_{k=1..8} L_(i,i-k) y_(i-k)); backward: x_i = L_ii^-T (y_i - sum_k
+    // L_(i+k,i)^T x_(i+k)).  The eight off-diagonal blocks and the diagonal block of a step are staged in
+    // shared memory by all threads at once; y and x of the last eight block rows live there too.
+    __shared__ float Bs[kBandBlocks][9 * 9];                  // [0] diagonal, [k] block k of the step
+    __shared__ float win[kBandBlocks][9];                     // solution of block rows i-1.. / i+1.. (ring by i % 9)
     float* y = v.tmp;
     for (int i = 0; i < nf; i++) {
+        for (int idx = tid; idx < kBandBlocks * pp; idx += nt) {
+            const int k = idx / pp, e = idx - k * pp;
+            if (i - k >= 0) Bs[k][e] = L[((size_t)i * kBandBlocks + k) * pp + e];
+        }
+        __syncthreads();
         if (tid < p) {
             float s = v.jtr[i * p + tid];
             for (int k = 1; k < kBandBlocks && i - k >= 0; k++) {
-                const float* B = L + ((size_t)i * kBandBlocks + k) * pp + tid * p;
-                const float* yk = y + (i - k) * p;
-                for (int q = 0; q < p; q++) s -= B[q] * yk[q];
+                const float* yk = win[(i - k) % kBandBlocks];
+                for (int q = 0; q < p; q++) s -= Bs[k][tid * p + q] * yk[q];
             }
             sm[tid] = s;
         }
         __syncthreads();
         if (tid == 0) {
-            const float* D = L + ((size_t)i * kBandBlocks) * pp;
+            float* yi = win[i % kBandBlocks];
             for (int r = 0; r < p; r++) {
                 float s = sm[r];
-                for (int j = 0; j < r; j++) s -= D[r * p + j] * y[i * p + j];
-                y[i * p + r] = s / D[r * p + r];
+                for (int j = 0; j < r; j++) s -= Bs[0][r * p + j] * yi[j];
+                yi[r] = s / Bs[0][r * p + r];
+                y[i * p + r] = yi[r];
             }
         }
         __syncthreads();
     }
-    // backward: x_i = L_ii^-T (y_i - sum_{k=1..8} L_(i+k,i)^T x_(i+k))
     float* x = v.step;
     for (int i = nf - 1; i >= 0; i--) {
+        for (int idx = tid; idx < kBandBlocks * pp; idx += nt) {
+            const int k = idx / pp, e = idx - k * pp;
+            if (k == 0) Bs[0][e] = L[((size_t)i * kBandBlocks) * pp + e];
+            else if (i + k < nf) Bs[k][e] = L[((size_t)(i + k) * kBandBlocks + k) * pp + e];   // block (i+k, i)
+        }
+        __syncthreads();
         if (tid < p) {
             float s = y[i * p + tid];
             for (int k = 1; k < kBandBlocks && i + k < nf; k++) {
-                const float* B = L + ((size_t)(i + k) * kBandBlocks + k) * pp;   // block (i+k, i)
-                const float* xk = x + (i + k) * p;
-                for (int q = 0; q < p; q++) s -= B[q * p + tid] * xk[q];
+                const float* xk = win[(i + k) % kBandBlocks];
+                for (int q = 0; q < p; q++) s -= Bs[k][q * p + tid] * xk[q];
             }
             sm[tid] = s;
         }
         __syncthreads();
         if (tid == 0) {
-            const float* D = L + ((size_t)i * kBandBlocks) * pp;
+            float* xi = win[i % kBandBlocks];
             for (int r = p - 1; r >= 0; r--) {
                 float s = sm[r];
-                for (int j = r + 1; j < p; j++) s -= D[j * p + r] * x[i * p + j];
-                x[i * p + r] = s / D[r * p + r];
+                for (int j = r + 1; j < p; j++) s -= Bs[0][j * p + r] * xi[j];
+                xi[r] = s / Bs[0][r * p + r];
+                x[i * p + r] = xi[r];
             }
         }
         __syncthreads();
