@@ -139,7 +139,7 @@ class RefineProblem:
         res, ok = self.residuals(traj)
         r2 = (res[:, 0] * res[:, 0] + res[:, 1] * res[:, 1]).astype(F)
         l = loss.loss(r2)
-        cost = F(0.0)
+        terms = np.zeros(len(self.edges), F)
         for e in range(len(self.edges)):
             ew = self.edge_weight(e)
             sel = (self.e_id == e) & ok
@@ -147,8 +147,8 @@ class RefineProblem:
             ec = pnp.seq_sum(l[sel]) if n else F(0.0)
             if n:
                 ec = F(ec / F(n))
-            cost = F(cost + F(ew * ec))
-        return cost
+            terms[e] = F(ew * ec)
+        return F(pnp.seq_sum(terms))
 
     def residuals_jac(self, traj):
         """EvaluateWithJacobian for every residual (refiner.cc:363-506).
@@ -252,8 +252,9 @@ class RefineProblem:
         res, Js, Jt, ok = self.residuals_jac(traj)
         r2 = (res[:, 0] * res[:, 0] + res[:, 1] * res[:, 1]).astype(F)
         lw = loss.weight(r2)
-        A = np.zeros((nf * p, nf * p), F)
-        g = np.zeros(nf * p, F)
+        acc = pnp._SUM["dtype"]                                  # float32 like the reference unless a test asks for exact sums
+        A = np.zeros((nf * p, nf * p), acc)
+        g = np.zeros(nf * p, acc)
         for e, ed in enumerate(self.edges):
             ew = self.edge_weight(e)
             if ew == 0:
@@ -278,7 +279,7 @@ class RefineProblem:
                 A[b2:b2 + p, b1:b1 + p] += JtJ[p:, :p]
             g[b1:b1 + p] += Jtr[:p]
             g[b2:b2 + p] += Jtr[p:]
-        return A, g
+        return A.astype(F), g.astype(F)
 
     def step(self, traj, dp):                                    # refiner.cc:508-537,618-646
         out = [c.copy() for c in traj]

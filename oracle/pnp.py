@@ -1,8 +1,9 @@
 """float32 restatement of the reference's per-frame pose solve -- TEST INFRASTRUCTURE.
 
 PARITY UNPINNED: the reference ships no test or golden vector for this path and cannot be compiled
-here (Eigen is absent); checked only by analytic-vs-numeric Jacobians, the one known-answer LLT example of
-cpp/examples/levmarq_ill_conditioned_float32_issue.cpp and ground-truth recovery (tests/test_oracle_solvers.py).
+here (Eigen is absent); checked only by analytic-vs-numeric Jacobians, ground-truth recovery and the one
+known-answer LLT example of cpp/examples/levmarq_ill_conditioned_float32_issue.cpp, whose recorded digits
+no restated Eigen build variant reproduces (oracle/eigen_llt.py, tests/test_oracle_solvers.py).
 
   robust losses        /root/reference/cpp/pnp/robust_loss.h:47-104
   PnPProblem           /root/reference/cpp/pnp/pnp_problem.h:13-142
@@ -12,6 +13,7 @@ Sums are formed sequentially in residual order in float32 (what the reference do
 max_allowed_parallelism = 1)."""
 from __future__ import annotations
 
+from contextlib import contextmanager
 from dataclasses import dataclass
 
 import numpy as np
@@ -74,37 +76,49 @@ class Loss:
             return np.maximum(FLT_MIN, F(1.0) / (F(1.0) + r2 * self.inv_sq_thr)).astype(F)
 
 
+_SUM = {"dtype": F, "rng": None}
+
+
+@contextmanager
+def summation(dtype=F, perm_seed=None):
+    """How seq_sum accumulates inside the block.  Default: sequential float32 in residual order (the
+    reference with max_allowed_parallelism = 1).  dtype=np.float64: correctly rounded sums (the
+    order-independent value every float32 order scatters around).  perm_seed: sequential float32
+    over a random permutation of the terms -- one sample of the reference's own nondeterminism (its
+    TBB reductions combine thread-local partial sums in scheduling order, lev_marq.h:231-297,
+    653-771); tests use a few seeds to measure that noise band."""
+    old = dict(_SUM)
+    _SUM["dtype"] = dtype
+    _SUM["rng"] = None if perm_seed is None else np.random.default_rng(perm_seed)
+    try:
+        yield
+    finally:
+        _SUM.update(old)
+
+
 def seq_sum(a, axis=0):
-    """Sequential float32 accumulation along axis 0 (TBB with one thread)."""
+    """Accumulation along axis 0: sequential float32 (TBB with one thread) unless `summation` says otherwise."""
+    assert axis == 0
     a = np.asarray(a, F)
-    return np.add.accumulate(a, axis=axis, dtype=F)[-1] if a.shape[axis] else np.zeros(a.shape[1:], F)
+    if not a.shape[0]:
+        return np.zeros(a.shape[1:], F)
+    if _SUM["rng"] is not None:
+        a = a[_SUM["rng"].permutation(a.shape[0])]
+    if _SUM["dtype"] is np.float64:
+        return a.sum(axis=0, dtype=np.float64).astype(F)
+    return np.add.accumulate(a, axis=0, dtype=F)[-1]
 
 
 def llt_lower(A):
-    """Eigen::LLT<Lower> on a float32 matrix (lower triangle referenced).  Returns (L, ok)."""
-    n = A.shape[0]
-    L = np.tril(np.array(A, F, copy=True))
-    for k in range(n):
-        x = F(L[k, k] - F(np.dot(L[k, :k], L[k, :k]))) if k else L[k, k]
-        if not (x > 0):
-            return L, False
-        x = F(np.sqrt(x))
-        L[k, k] = x
-        if k + 1 < n:
-            if k:
-                L[k + 1:, k] = (L[k + 1:, k] - L[k + 1:, :k] @ L[k, :k]).astype(F)
-            L[k + 1:, k] = (L[k + 1:, k] / x).astype(F)
-    return L, True
+    """Eigen::LLT<Lower> on a float32 row-major matrix (lower triangle referenced), in Eigen 3.4's
+    operation order (oracle/eigen_llt.py).  Returns (L, ok)."""
+    from . import eigen_llt
+    return eigen_llt.llt_lower(A)
 
 
 def llt_solve(L, b):
-    n = len(b)
-    y = np.array(b, F, copy=True)
-    for i in range(n):
-        y[i] = F((y[i] - F(np.dot(L[i, :i], y[:i]))) / L[i, i])
-    for i in range(n - 1, -1, -1):
-        y[i] = F((y[i] - F(np.dot(L[i + 1:, i], y[i + 1:]))) / L[i, i])
-    return y
+    from . import eigen_llt
+    return eigen_llt.llt_solve(L, b)
 
 
 class PnPProblem:

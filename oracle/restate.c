@@ -188,6 +188,11 @@ static inline int descale(int x, int n) { return (x + (1 << (n - 1))) >> n; }
 /* Track n points through `nlevels` levels (index 0 = full resolution).
  * win = window size (square), iters/eps = TermCriteria, min_eig = minEigThreshold.
  * Outputs next (x,y), status, err exactly as cv::calcOpticalFlowPyrLK lays them out. */
+/* Optional trace (scheduling studies of the CUDA kernel, scripts/lk_sched_sim.py): when set, element
+ * [pi * nlevels + level] receives the number of window passes the point ran at that level. */
+int* orc_lk_iter_trace = 0;
+void orc_lk_set_iter_trace(int* p) { orc_lk_iter_trace = p; }
+
 void orc_lk(const orc_level* L1, const orc_level* L2, int nlevels, const float* pts, int n,
             int win, int iters, double eps, double min_eig_thr, float* next, uint8_t* status, float* err) {
     const int W_BITS = 14;
@@ -316,6 +321,7 @@ void orc_lk(const orc_level* L1, const orc_level* L2, int nlevels, const float* 
                 }
                 pdx = dx; pdy = dy;
             }
+            if (orc_lk_iter_trace) orc_lk_iter_trace[pi * nlevels + level] = j < iters ? j + 1 : iters;
             if (status[pi] && level == 0) {
                 float fx = next[2 * pi] - halfw, fy = next[2 * pi + 1] - halfw;
                 int inx = (int)floorf(fx), iny = (int)floorf(fy);

@@ -171,6 +171,9 @@ static int run_detector(pc_ctx* c, FrameSlot* f, const pc_gftt_opts* go, cudaStr
     launch_select(c->cand, c->cand_count, c->cand_cap, c->eig, c->eig_pitch, c->state, c->state_pitch, f->w, f->h,
                   go->min_distance, go->max_corners, ws, f->kps, c->lim.max_features, f->n_kps, c->sm_count, s);
     span_end(c, s);
+    // the candidate count lives in the shared detector scratch, which the next frame's detector clears: keep
+    // this frame's value with its other counters so that an overflow is still seen when the frame is popped
+    PC_CUDA(c, cudaMemcpyAsync(f->n_kps + 3, c->cand_count, sizeof(int), cudaMemcpyDeviceToDevice, s));
     f->has_kps = true;
     f->n_kps_host = -1;
     return check_launch(c, "detector", 6);
@@ -609,8 +612,8 @@ int pc_set_keypoints(pc_ctx* c, int32_t frame_id, const float* kps, int n) {
     if (!f) return fail(c, PC_ERR_NOT_FOUND, "frame " + std::to_string(frame_id) + " is not resident");
     PC_CHECK(c, n >= 0 && (n == 0 || kps != nullptr), "bad keypoint array");
     if (n > c->lim.max_features) return fail(c, PC_ERR_CAPACITY, "more keypoints than the context's max_features");
-    int hdr[3] = {n, n, 0};
-    PC_CUDA(c, cudaMemcpyAsync(f->kps, kps, sizeof(float) * 2 * n, cudaMemcpyHostToDevice, c->compute));
+    int hdr[4] = {n, n, 0, 0};
+    if (n) PC_CUDA(c, cudaMemcpyAsync(f->kps, kps, sizeof(float) * 2 * n, cudaMemcpyHostToDevice, c->compute));
     PC_CUDA(c, cudaMemcpyAsync(f->n_kps, hdr, sizeof(hdr), cudaMemcpyHostToDevice, c->compute));
     PC_CUDA(c, cudaStreamSynchronize(c->compute));
     f->has_kps = true;
@@ -865,7 +868,7 @@ static int enqueue_lk(pc_ctx* c, Stage& st, FrameSlot* f) {
     if (rc) return rc;
     // results -> pinned host, on the download stream
     PC_CUDA(c, cudaStreamWaitEvent(c->d2h, st.computed, 0));
-    PC_CUDA(c, cudaMemcpyAsync(st.counts_host, f->n_kps, sizeof(int) * 3, cudaMemcpyDeviceToHost, c->d2h));
+    PC_CUDA(c, cudaMemcpyAsync(st.counts_host, f->n_kps, sizeof(int) * 4, cudaMemcpyDeviceToHost, c->d2h));
     st.rows_downloaded = false;
     if (c->download_hint && st.rows_bytes <= kSlabCopyMax && batch.cap <= c->lim.max_features) {
         // the caller has been taking rows: send the whole slab (counts + rows) and the keypoints now,
@@ -921,12 +924,12 @@ int pc_analyze_push_frame(pc_ctx* c, int32_t frame_id, const uint8_t* rgb, size_
         st.gray_pending = true;
     }
     auto preset = c->preset_kps.find(frame_id);
-    if (preset != c->preset_kps.end() && !preset->second.empty()) {   // ReadOrGenerateKeypoints
+    if (preset != c->preset_kps.end()) {   // ReadOrGenerateKeypoints: a stored row is used as it is, even when empty
         const int n = (int)(preset->second.size() / 2);
-        int hdr[3] = {n, n, 0};
-        memcpy(st.kps_host, preset->second.data(), sizeof(float) * 2 * n);
+        int hdr[4] = {n, n, 0, 0};
+        if (n) memcpy(st.kps_host, preset->second.data(), sizeof(float) * 2 * n);
         memcpy(st.counts_host, hdr, sizeof(hdr));
-        PC_CUDA(c, cudaMemcpyAsync(f->kps, st.kps_host, sizeof(float) * 2 * n, cudaMemcpyHostToDevice, c->compute));
+        if (n) PC_CUDA(c, cudaMemcpyAsync(f->kps, st.kps_host, sizeof(float) * 2 * n, cudaMemcpyHostToDevice, c->compute));
         PC_CUDA(c, cudaMemcpyAsync(f->n_kps, st.counts_host, sizeof(hdr), cudaMemcpyHostToDevice, c->compute));
         f->has_kps = true;
         f->n_kps_host = n;
@@ -956,7 +959,7 @@ int pc_analyze_pop(pc_ctx* c, pc_frame_result* out, int download) {
     memset(out, 0, sizeof(*out));
     out->frame_id = st.frame_id;
     const int n_kps = st.counts_host[0];
-    int rc = check_detector_result(c, &c->gopts, n_kps, st.counts_host[1], st.counts_host[2], 0);
+    int rc = check_detector_result(c, &c->gopts, n_kps, st.counts_host[1], st.counts_host[2], st.counts_host[3]);
     if (rc) { c->inflight.pop_front(); st.busy = false; return rc; }
     out->num_keypoints = n_kps;
     out->num_pairs = st.num_pairs;

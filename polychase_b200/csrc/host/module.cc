@@ -73,6 +73,15 @@ static Frame FrameFromNumpy(const U8Arr& a) {
     return f;
 }
 
+// Holder for a Python callable that is shared with code running without the GIL (the pipelines release
+// it): the last reference may die on any thread, so the deleter takes the GIL before the decref.
+static std::shared_ptr<py::function> HoldPy(py::function fn) {
+    return std::shared_ptr<py::function>(new py::function(std::move(fn)), [](py::function* p) {
+        py::gil_scoped_acquire gil;
+        delete p;
+    });
+}
+
 template <typename Variant>
 static py::object VariantToPy(std::optional<Variant> m) {
     if (!m) return py::none();
@@ -347,7 +356,9 @@ PYBIND11_MODULE(polychase_core, m) {
 
     m.def("ray_cast",
           [](const AcceleratedMesh& mesh, const SceneTransformations& scene, const FArr& pos, bool check_mask) {
-              return mesh.RayCast(scene, ArrFromNumpy<2>(pos), check_mask);
+              const auto p = ArrFromNumpy<2>(pos);
+              py::gil_scoped_release release;      // the device round trip runs without the GIL
+              return mesh.RayCast(scene, p, check_mask);
           },
           py::arg("accel_mesh"), py::arg("scene_transform"), py::arg("pos"), py::arg("check_mask"));
 
@@ -355,9 +366,12 @@ PYBIND11_MODULE(polychase_core, m) {
           [](const VideoInfo& vi, py::function accessor, py::object callback, const std::string& path,
              const GFTTOptions& go, const OpticalFlowOptions& fo, bool write_images) {
               // Python callables are invoked with the GIL re-acquired; the pipeline itself runs without it
-              FrameAccessorFunction acc = [accessor](int32_t frame_id) -> std::optional<Frame> {
+              // Python callables live behind a shared_ptr whose deleter takes the GIL: copying or destroying the
+              // std::function that captures it never touches a Python reference count without the GIL
+              auto accessor_h = HoldPy(std::move(accessor));
+              FrameAccessorFunction acc = [accessor_h](int32_t frame_id) -> std::optional<Frame> {
                   py::gil_scoped_acquire gil;
-                  py::object r = accessor(frame_id);
+                  py::object r = (*accessor_h)(frame_id);
                   if (r.is_none()) return std::nullopt;
                   auto arr = std::make_shared<U8Arr>(r.cast<U8Arr>());
                   Frame f = FrameFromNumpy(*arr);
@@ -373,10 +387,10 @@ PYBIND11_MODULE(polychase_core, m) {
               };
               OpticalFlowProgressCallback cb;
               if (!callback.is_none()) {
-                  py::function fn = callback.cast<py::function>();
+                  auto fn = HoldPy(callback.cast<py::function>());
                   cb = [fn](float p, const std::string& msg) {
                       py::gil_scoped_acquire gil;
-                      return fn(p, msg).cast<bool>();
+                      return (*fn)(p, msg).cast<bool>();
                   };
               }
               py::gil_scoped_release release;
@@ -391,10 +405,10 @@ PYBIND11_MODULE(polychase_core, m) {
              const AcceleratedMesh& mesh, py::object callback, bool of, bool opp, BundleOptions bo) {
               TrackingCallback cb;
               if (!callback.is_none()) {
-                  py::function fn = callback.cast<py::function>();
+                  auto fn = HoldPy(callback.cast<py::function>());
                   cb = [fn](const FrameTrackingResult& r) {
                       py::gil_scoped_acquire gil;
-                      return fn(r).cast<bool>();
+                      return (*fn)(r).cast<bool>();
                   };
               }
               py::gil_scoped_release release;
@@ -409,10 +423,10 @@ PYBIND11_MODULE(polychase_core, m) {
              bool opp, py::object callback, BundleOptions bo) {
               RefineTrajectoryCallback cb;
               if (!callback.is_none()) {
-                  py::function fn = callback.cast<py::function>();
+                  auto fn = HoldPy(callback.cast<py::function>());
                   cb = [fn](RefineTrajectoryUpdate u) {
                       py::gil_scoped_acquire gil;
-                      return fn(u).cast<bool>();
+                      return (*fn)(u).cast<bool>();
                   };
               }
               const Mat4 mm = Mat4FromNumpy(model);

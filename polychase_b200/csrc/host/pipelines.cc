@@ -131,8 +131,8 @@ class FlowWriter {
 // detection once per frame, all pairs whose later frame just arrived in one LK launch) and the
 // finished rows are written behind the GPU.  The database ends up with the same rows: one
 // keypoints row per frame, one optical_flow row per directed pair inside [first, first+num).
-void GenerateOpticalFlowDatabase(const VideoInfo& video_info, FrameAccessorFunction frame_accessor,
-                                 OpticalFlowProgressCallback callback, const std::string& database_path,
+void GenerateOpticalFlowDatabase(const VideoInfo& video_info, const FrameAccessorFunction& frame_accessor,
+                                 const OpticalFlowProgressCallback& callback, const std::string& database_path,
                                  const GFTTOptions& detector_options, const OpticalFlowOptions& flow_options,
                                  bool write_images) {
     PCH_CHECK(frame_accessor);                                            // opticalflow.cc:216
@@ -142,8 +142,14 @@ void GenerateOpticalFlowDatabase(const VideoInfo& video_info, FrameAccessorFunct
     const int32_t to = video_info.first_frame + (int32_t)video_info.num_frames;
 
     const int w = (int)video_info.width, h = (int)video_info.height;
-    int max_features = detector_options.max_corners > 0 ? detector_options.max_corners
-                                                        : std::max(16384, (int)(((int64_t)w * h) / 16));
+    // max_corners == 0 means unlimited (gftt.h:10): corners at least min_distance apart cannot be denser than
+    // a hexagonal packing (1.155 w h / d^2), and 3x3 NMS leaves at most one candidate per 2x2 block
+    int max_features = detector_options.max_corners;
+    if (max_features <= 0) {
+        const double d = std::max(1.0, detector_options.min_distance);
+        const double bound = std::min((double)w * h / 4.0, 1.2 * (double)w * h / (d * d) + 1024.0);
+        max_features = std::max(16384, (int)bound);
+    }
     // Resume: keypoints already in the database are used as they are (they may be more numerous than
     // max_corners).  They are read now, because once the write-behind thread runs the connection is its.
     std::map<int32_t, Keypoints> stored_kps;
@@ -151,7 +157,9 @@ void GenerateOpticalFlowDatabase(const VideoInfo& video_info, FrameAccessorFunct
         if (!db.KeypointsExist(f)) continue;
         Keypoints kps = db.ReadKeypoints(f);
         max_features = std::max(max_features, (int)kps.size());
-        if (!kps.empty()) stored_kps.emplace(f, std::move(kps));
+        // a stored row is authoritative even when it is empty (ReadOrGenerateKeypoints, opticalflow.cc:168-178:
+        // the reference only detects when no row exists), so flows never index keypoints that are not in the database
+        stored_kps.emplace(f, std::move(kps));
     }
     auto dc = AcquireDeviceContext(w, h, max_features);
     pc_ctx* ctx = dc->ctx;
@@ -203,7 +211,8 @@ void GenerateOpticalFlowDatabase(const VideoInfo& video_info, FrameAccessorFunct
         PCH_CHECK((uint32_t)frame->width == video_info.width);
         const auto stored = stored_kps.find(frame_id);
         if (stored != stored_kps.end())
-            Check(ctx, pc_analyze_preset_keypoints(ctx, frame_id, stored->second[0].data(), (int)stored->second.size()));
+            Check(ctx, pc_analyze_preset_keypoints(ctx, frame_id, stored->second.empty() ? nullptr : stored->second[0].data(),
+                                                   (int)stored->second.size()));
         if (pc_analyze_pending(ctx) >= 3) drain_one();
         Check(ctx, pc_analyze_push_frame(ctx, frame_id, frame->data, frame->stride,
                                          frame->pinned ? PC_MEM_HOST_PINNED : PC_MEM_HOST));
@@ -278,7 +287,7 @@ std::optional<PnPResult> SolveFrame(DeviceContext& dc, const Database& database,
 
 void TrackCameraTrajectory(const Database& database, CameraTrajectory& camera_traj, int32_t frame_from,
                            int32_t frame_to_inclusive, const Mat4& model_matrix, const AcceleratedMesh& accel_mesh,
-                           TrackingCallback callback, bool optimize_focal_length, bool optimize_principal_point,
+                           const TrackingCallback& callback, bool optimize_focal_length, bool optimize_principal_point,
                            const BundleOptions& opts) {
     const int32_t first_frame = std::min(frame_from, frame_to_inclusive);
     const int32_t last_frame = std::max(frame_from, frame_to_inclusive);
@@ -288,12 +297,16 @@ void TrackCameraTrajectory(const Database& database, CameraTrajectory& camera_tr
     PCH_CHECK(camera_traj.IsFrameFilled(frame_from));
 
     auto dc = AcquireDeviceContext(0, 0, 0);
-    std::lock_guard<std::mutex> lk(dc->mtx);
-    accel_mesh.Bind(*dc);
+    // the context is locked per frame and released around the user callback: a callback that calls back
+    // into this module (or a Python callback waiting for the GIL) must not hold up other users of the context
+    std::unique_lock<std::mutex> lk(dc->mtx);
     SolveFrameCache cache;
     for (int32_t frame_id = frame_from + dir; frame_id != frame_to_inclusive + dir; frame_id += dir) {
+        if (!lk.owns_lock()) lk.lock();
+        accel_mesh.Bind(*dc);                                             // no-op while this mesh is the context's current one
         const std::optional<PnPResult> maybe = SolveFrame(*dc, database, camera_traj, model_matrix, frame_id,
                                                           optimize_focal_length, optimize_principal_point, opts, cache);
+        lk.unlock();
         if (!maybe)                                                       // :162-166
             throw std::runtime_error(Format("Could not track to frame: %d. Not enough features.", frame_id));
         if (callback) {
@@ -311,7 +324,7 @@ void TrackCameraTrajectory(const Database& database, CameraTrajectory& camera_tr
 
 void TrackSequence(const std::string& database_path, int32_t frame_from, int32_t frame_to_inclusive,
                    const SceneTransformations& scene_transform, const AcceleratedMesh& accel_mesh,
-                   TrackingCallback callback, bool optimize_focal_length, bool optimize_principal_point,
+                   const TrackingCallback& callback, bool optimize_focal_length, bool optimize_principal_point,
                    BundleOptions bundle_opts) {
     const Database database{database_path};
     const size_t num_frames = (size_t)std::abs(frame_to_inclusive - frame_from) + 1;
@@ -355,7 +368,7 @@ Bbox2 ComputeBbox(const CameraState& state, const Mesh& mesh, const Mat4& model_
 
 void RefineTrajectory(const std::string& database_path, CameraTrajectory& traj, const Mat4& model_matrix,
                       const AcceleratedMesh& mesh, bool optimize_focal_length, bool optimize_principal_point,
-                      RefineTrajectoryCallback callback, BundleOptions bundle_opts) {
+                      const RefineTrajectoryCallback& callback, BundleOptions bundle_opts) {
     Database database{database_path};
     PCH_CHECK(traj.Count() > 2);                                          // refiner.cc:661
     for (int32_t frame = traj.FirstFrame(); frame <= traj.LastFrame(); frame++) PCH_CHECK(traj.IsFrameFilled(frame));
@@ -425,7 +438,7 @@ void RefineTrajectory(const std::string& database_path, CameraTrajectory& traj, 
     std::vector<pc_camera_state> states(nf);
     for (int f = 0; f < nf; f++) states[f] = ToAbi(*traj.Get(traj.FirstFrame() + f));
     struct CbData {
-        RefineTrajectoryCallback* cb;
+        const RefineTrajectoryCallback* cb;
         size_t max_iterations;
     } cbd{&callback, bundle_opts.max_iterations};
     auto trampoline = [](const pc_bundle_stats* s, void* user) -> int {   // refiner.cc:670-678
@@ -435,6 +448,9 @@ void RefineTrajectory(const std::string& database_path, CameraTrajectory& traj, 
         u.progress = static_cast<float>(s->iterations) / d->max_iterations;
         u.message = Format("Cost: %.02f (Initial: %.02f)", s->cost, s->initial_cost);
         u.stats = FromAbi(*s);
+        // The context stays locked: the loaded refine problem lives in it and must not be replaced mid-solve.
+        // Nothing that holds the GIL takes this mutex (interactive ray casts use their own context,
+        // types.cc::AcquireInteractiveContext), so a Python callback cannot deadlock against it.
         return (*d->cb)(u) ? 1 : 0;
     };
     const pc_bundle_opts bo = ToAbi(bundle_opts);

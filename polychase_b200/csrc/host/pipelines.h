@@ -25,8 +25,10 @@ struct Frame {
 using FrameAccessorFunction = std::function<std::optional<Frame>(int32_t frame_id)>;
 using OpticalFlowProgressCallback = std::function<bool(float progress, const std::string& progress_message)>;
 
-void GenerateOpticalFlowDatabase(const VideoInfo& video_info, FrameAccessorFunction frame_accessor,
-                                 OpticalFlowProgressCallback callback, const std::string& database_path,
+// Callbacks are taken by const reference and never copied: a std::function that wraps a Python callable
+// must not be copied or destroyed on a thread that does not hold the GIL (module.cc).
+void GenerateOpticalFlowDatabase(const VideoInfo& video_info, const FrameAccessorFunction& frame_accessor,
+                                 const OpticalFlowProgressCallback& callback, const std::string& database_path,
                                  const GFTTOptions& detector_options = {}, const OpticalFlowOptions& flow_options = {},
                                  bool write_images = false);
 
@@ -41,12 +43,12 @@ using TrackingCallback = std::function<bool(const FrameTrackingResult&)>;
 
 void TrackSequence(const std::string& database_path, int32_t frame_from, int32_t frame_to_inclusive,
                    const SceneTransformations& scene_transform, const AcceleratedMesh& accel_mesh,
-                   TrackingCallback callback, bool optimize_focal_length, bool optimize_principal_point,
+                   const TrackingCallback& callback, bool optimize_focal_length, bool optimize_principal_point,
                    BundleOptions opts);
 
 void TrackCameraTrajectory(const Database& database, CameraTrajectory& camera_traj, int32_t frame_from,
                            int32_t frame_to_inclusive, const Mat4& model_matrix, const AcceleratedMesh& accel_mesh,
-                           TrackingCallback callback, bool optimize_focal_length, bool optimize_principal_point,
+                           const TrackingCallback& callback, bool optimize_focal_length, bool optimize_principal_point,
                            const BundleOptions& opts);
 
 struct RefineTrajectoryUpdate {
@@ -58,6 +60,6 @@ using RefineTrajectoryCallback = std::function<bool(RefineTrajectoryUpdate)>;
 
 void RefineTrajectory(const std::string& database_path, CameraTrajectory& traj, const Mat4& model_matrix,
                       const AcceleratedMesh& mesh, bool optimize_focal_length, bool optimize_principal_point,
-                      RefineTrajectoryCallback callback, BundleOptions bundle_opts);
+                      const RefineTrajectoryCallback& callback, BundleOptions bundle_opts);
 
 }  // namespace pch

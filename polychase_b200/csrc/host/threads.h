@@ -63,7 +63,8 @@ struct OpticalFlowRequest {
 using OpticalFlowThreadMessage = std::variant<OpticalFlowProgress, OpticalFlowRequest, bool, CppException>;
 
 // Page-locked frame buffers for the OpticalFlowThread hand-off, allocated through the C ABI on the
-// process-wide solver context (page-locked memory is usable by every context of the device).
+// process-wide interactive context, under its mutex (page-locked memory is usable by every context
+// of the device).
 class PinnedFrameRing {
    public:
     static constexpr int kFrameRing = 6;
@@ -74,14 +75,19 @@ class PinnedFrameRing {
         if (bytes != bytes_) {
             Release();
             try {
-                dc_ = AcquireDeviceContext(0, 0, 0);
+                dc_ = AcquireInteractiveContext();
             } catch (...) {
                 failed_ = true;
                 return nullptr;
             }
             for (int i = 0; i < kFrameRing; i++) {
                 void* p = nullptr;
-                if (pc_host_alloc_pinned(dc_->ctx, bytes, &p) != PC_OK) {
+                int rc;
+                {
+                    std::lock_guard<std::mutex> lk(dc_->mtx);
+                    rc = pc_host_alloc_pinned(dc_->ctx, bytes, &p);
+                }
+                if (rc != PC_OK) {
                     Release();
                     failed_ = true;
                     return nullptr;
@@ -98,7 +104,10 @@ class PinnedFrameRing {
    private:
     void Release() {
         for (auto& p : slots_) {
-            if (p && dc_) pc_host_free_pinned(dc_->ctx, p);
+            if (p && dc_) {
+                std::lock_guard<std::mutex> lk(dc_->mtx);
+                pc_host_free_pinned(dc_->ctx, p);
+            }
             p = nullptr;
         }
         bytes_ = 0;

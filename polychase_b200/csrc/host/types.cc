@@ -121,6 +121,25 @@ std::shared_ptr<DeviceContext> AcquireDeviceContext(int max_width, int max_heigh
     return dc;
 }
 
+std::shared_ptr<DeviceContext> AcquireInteractiveContext() {
+    static std::mutex g_mtx;
+    static std::weak_ptr<DeviceContext> g_interactive;
+    std::lock_guard<std::mutex> lk(g_mtx);
+    if (auto sp = g_interactive.lock()) return sp;
+    auto dc = std::make_shared<DeviceContext>();
+    pc_limits lim{};
+    lim.device = EnvDevice();
+    lim.max_width = 64;
+    lim.max_height = 64;
+    lim.max_features = 1024;
+    lim.ring_frames = 10;
+    lim.pipeline_depth = 1;
+    const int rc = pc_create(&lim, &dc->ctx);
+    if (rc != PC_OK) throw std::runtime_error(pc_last_error(nullptr));
+    g_interactive = dc;
+    return dc;
+}
+
 static std::atomic<uint64_t> g_mesh_epoch{1};
 
 AcceleratedMesh::AcceleratedMesh(std::vector<float> vertices, std::vector<uint32_t> triangles,
@@ -130,17 +149,21 @@ AcceleratedMesh::AcceleratedMesh(std::vector<float> vertices, std::vector<uint32
 }
 
 void AcceleratedMesh::Bind(DeviceContext& dc) const {
-    if (dc.mesh_epoch == epoch_ && !mask_dirty_) return;
+    if (dc.mesh_epoch == epoch_) return;
     const int rc = pc_mesh_set(dc.ctx, mesh_.vertices.data(), (int)mesh_.NumVertices(), mesh_.triangles.data(),
                                (int)mesh_.NumTriangles(), mesh_.masked_triangles.data(),
                                (int)mesh_.masked_triangles.size());
     if (rc != PC_OK) ThrowPcError(dc.ctx, rc);
     dc.mesh_epoch = epoch_;
-    mask_dirty_ = false;
+}
+
+Mesh& AcceleratedMesh::InnerMut() {
+    epoch_ = g_mesh_epoch++;
+    return mesh_;
 }
 
 std::optional<RayHit> AcceleratedMesh::RayCast(const SceneTransformations& scene, Vec2 pos, bool check_mask) const {
-    auto dc = AcquireDeviceContext(0, 0, 0);
+    auto dc = AcquireInteractiveContext();
     std::lock_guard<std::mutex> lk(dc->mtx);
     Bind(*dc);
     CameraState cs{scene.intrinsics, Pose::FromRt(scene.view_matrix)};

@@ -193,6 +193,10 @@ struct DeviceContext {
     ~DeviceContext();
 };
 std::shared_ptr<DeviceContext> AcquireDeviceContext(int max_width, int max_height, int max_features);
+// The context of the interactive entry points (ray_cast from the UI thread, pinned frame buffers):
+// separate from the solver context, so a UI ray cast never waits for a running track / refine pass
+// (the reference's Embree ray cast is independent of its solvers too, ray_casting.cc:128-133).
+std::shared_ptr<DeviceContext> AcquireInteractiveContext();
 [[noreturn]] void ThrowPcError(pc_ctx* ctx, int code);
 
 class AcceleratedMesh {                          // ray_casting.h:23-50; BVH lives on the GPU
@@ -202,7 +206,7 @@ class AcceleratedMesh {                          // ray_casting.h:23-50; BVH liv
     AcceleratedMesh(const AcceleratedMesh&) = delete;
     AcceleratedMesh& operator=(const AcceleratedMesh&) = delete;
     const Mesh& Inner() const { return mesh_; }
-    Mesh& InnerMut() { mask_dirty_ = true; return mesh_; }
+    Mesh& InnerMut();    // the caller may edit the mask: every context re-uploads the mesh on its next Bind
     // Makes this mesh the context's current mesh (uploads + builds the BVH when needed).
     void Bind(DeviceContext& dc) const;
     std::optional<RayHit> RayCast(const SceneTransformations& scene, Vec2 pos, bool check_mask) const;
@@ -210,7 +214,6 @@ class AcceleratedMesh {                          // ray_casting.h:23-50; BVH liv
    private:
     Mesh mesh_;
     uint64_t epoch_;
-    mutable bool mask_dirty_ = false;
 };
 
 // conversions to the C ABI records

@@ -108,6 +108,7 @@ __global__ void __launch_bounds__(128) ba_refresh_kernel(BAView v, MeshView mesh
 }
 
 void launch_ba_refresh_points(const BAView& v, const MeshView& mesh, cudaStream_t s) {
+    if (v.n_kps <= 0) return;      // every keypoint fell outside the projected mesh bbox: nothing to evaluate
     ba_refresh_kernel<<<(v.n_kps + 127) / 128, 128, 0, s>>>(v, mesh);
 }
 

@@ -49,13 +49,23 @@ def rot_xyz(rx: float, ry: float, rz: float) -> np.ndarray:
     return Rz @ Ry @ Rx
 
 
-def camera_path(num_frames: int, depth: float = 4.0, first: int = 0):
+def survey_speed(width: int) -> float:
+    """Time scale of `camera_path` that keeps the largest image motion over 8 frames at about 20 px
+    for a `width`-pixel frame -- SURVEY.md section 8d: "max inter-frame flow at skip 8 <~ 20 px,
+    inside the 4-level pyramid's capture range".  At speed 1 the +-2 degree yaw/pitch sweeps move the
+    image by up to 89 px per 8 frames at 4K (f = 1.2 W = 4608 px: one degree is 80 px), which is
+    outside what a 4-level pyramid with 10x10 windows can follow: 54 % of the skip-4 and 96 % of the
+    skip-8 tracks then end more than 3 px from the true position (profiles/r2_lk_track_error_by_skip.txt)."""
+    return min(1.0, 20.0 / (89.3 * width / 3840.0))
+
+
+def camera_path(num_frames: int, depth: float = 4.0, first: int = 0, speed: float = 1.0):
     """Smooth object->camera poses (R, t), float64.  yaw/pitch +-2 deg, translation
-    <= 2% of depth per 8 frames."""
+    <= 2% of depth per 8 frames.  `speed` scales time (see survey_speed)."""
     Rs, ts = [], []
     for k in range(first, first + num_frames):
-        a = 2.0 * np.pi * k / 97.0
-        b = 2.0 * np.pi * k / 61.0
+        a = 2.0 * np.pi * k * speed / 97.0
+        b = 2.0 * np.pi * k * speed / 61.0
         R = rot_xyz(np.deg2rad(2.0) * np.sin(b), np.deg2rad(2.0) * np.sin(a),
                     np.deg2rad(1.0) * np.sin(0.5 * a))
         t = np.array([
@@ -141,14 +151,15 @@ class Clip:
     """A deterministic synthetic clip: frames on demand, ground-truth cameras, mesh."""
 
     def __init__(self, width: int, height: int, num_frames: int, seed: int = 0,
-                 first_frame: int = 0, depth: float = 4.0):
+                 first_frame: int = 0, depth: float = 4.0, speed: float = 1.0):
         self.width, self.height, self.num_frames = width, height, num_frames
         self.first_frame = first_frame
         self.depth = depth
         self.tex = make_texture(width, height, seed)
         self.K = intrinsics(width, height)
         self.s = plane_scale(width, depth)
-        self.R, self.t = camera_path(num_frames, depth, first_frame)
+        self.speed = speed
+        self.R, self.t = camera_path(num_frames, depth, first_frame, speed)
         self.verts, self.tris = plane_mesh(width, height, self.s)
 
     def homography(self, k: int) -> np.ndarray:

@@ -31,6 +31,9 @@ def main():
     ap.add_argument("--config", default="4k", choices=sorted(CONFIGS))
     ap.add_argument("--max-iterations", type=int, default=20)
     ap.add_argument("--reps", type=int, default=5, help="timed repetitions of the cost / build entry points")
+    ap.add_argument("--motion", default="survey", choices=["survey", "r1"],
+                    help="survey: image motion <~ 20 px per 8 frames (SURVEY.md 8d, synth.survey_speed); "
+                         "r1: round 1's path (up to 89 px per 8 frames at 4K, outside LK's capture range)")
     args = ap.parse_args()
 
     from polychase_b200 import synth  # input generator
@@ -44,7 +47,8 @@ def main():
     ctx.synth_set_texture(tex)
     K = synth.intrinsics(w, h)
     scale = synth.plane_scale(w, 4.0)
-    Rs, ts = synth.camera_path(F, 4.0, 0)
+    speed = synth.survey_speed(w) if args.motion == "survey" else 1.0
+    Rs, ts = synth.camera_path(F, 4.0, 0, speed)
     stride = w * 3
     frame_bytes = stride * h
     ring = 16
@@ -145,6 +149,7 @@ def main():
         "lambda": float(st.lambda_), "grad_norm": float(st.grad_norm), "step_norm": float(st.step_norm),
         "max_abs_t_err_before": e0[0], "max_abs_t_err_after": e1[0],
         "max_abs_q_err_before": e0[1], "max_abs_q_err_after": e1[1],
+        "motion": args.motion,
     }
     print(json.dumps(line))
     ctx.device_free(dev)

@@ -10,11 +10,30 @@ from oracle import synth
 F = np.float32
 
 
+# The addon's camera (blender_addon/core.py:348-357): OpenGL convention (looks down -Z,
+# cpp/pnp/types.h:13-16) with fx, fy negated, on images whose rows run bottom-up
+# (blender_addon/operators/analysis.py:220-233).  The same physical camera as the clip's OpenCV one:
+# camera axes turned by pi about x (y and z flip), image rows flipped (y -> H-1-y), so that
+#   fx_gl * Xg.x / Xg.z + cx = u   and   fy_gl * Xg.y / Xg.z + (H-1-cy) = H-1-v.
+GL_FLIP = np.diag([1.0, -1.0, -1.0])
+
+
 def oracle_cam(clip: synth.Clip, k: int, convention=G.OPENCV) -> G.CameraState:
     K = clip.K
     i = k - clip.first_frame
-    it = G.Intrinsics(K["fx"], K["fy"], K["cx"], K["cy"], 1.0, clip.width, clip.height, convention).f32()
-    return G.CameraState(it, G.Pose(G.quat_from_matrix(clip.R[i]).astype(F), clip.t[i].astype(F)))
+    if convention == G.OPENCV:
+        it = G.Intrinsics(K["fx"], K["fy"], K["cx"], K["cy"], 1.0, clip.width, clip.height, convention).f32()
+        return G.CameraState(it, G.Pose(G.quat_from_matrix(clip.R[i]).astype(F), clip.t[i].astype(F)))
+    it = G.Intrinsics(-K["fx"], -K["fy"], K["cx"], (clip.height - 1) - K["cy"], 1.0, clip.width, clip.height,
+                      G.OPENGL).f32()
+    return G.CameraState(it, G.Pose(G.quat_from_matrix(GL_FLIP @ clip.R[i]).astype(F),
+                                    (GL_FLIP @ clip.t[i]).astype(F)))
+
+
+def clip_rgb(clip: synth.Clip, k: int, convention=G.OPENCV) -> np.ndarray:
+    """Frame k as the given camera convention sees it (OpenGL: rows bottom-up, like Blender's buffers)."""
+    rgb = clip.rgb(k)
+    return rgb if convention == G.OPENCV else np.ascontiguousarray(rgb[::-1])
 
 
 def to_abi(cam: G.CameraState):

@@ -171,3 +171,117 @@ def test_optical_flow_thread_cancel(core, tmp_path):
             break
         last = m
     assert last is True
+
+
+def test_sync_entry_points_with_python_callbacks_opengl(core, tmp_path):
+    """generate_optical_flow_database / track_sequence / refine_trajectory (polychase_pybind.cc:313-347) called
+    with Python callables -- they run without the GIL and call back with it -- on the addon's own camera:
+    OpenGL convention, negated fx / fy, bottom-up frames (blender_addon/core.py:348-357), while another
+    Python thread ray-casts against the same mesh (the UI does that during tracking)."""
+    import threading
+    from oracle import geometry as G
+    w, h, NF, first = 320, 240, 12, 1
+    clip = synth.Clip(w, h, NF, seed=8, first_frame=first)
+    frames = {k: H.clip_rgb(clip, k, G.OPENGL) for k in range(first, first + NF)}
+    dbp = str(tmp_path / "sync.db")
+    go = core.GFTTOptions()
+    go.max_corners = 300
+    asked, prog = [], []
+
+    def accessor(frame_id):
+        asked.append(frame_id)
+        return frames[frame_id]
+
+    def progress(p, msg):
+        prog.append(msg)
+        return True
+
+    core.generate_optical_flow_database(core.VideoInfo(w, h, first, NF), accessor, progress, dbp, go)
+    assert asked == list(range(first, first + NF)) and prog[-1] == "Done"
+    o = odb.Database(dbp)
+    assert len(o.pairs()) == 8 * NF - 30
+    kps = {k: o.read_keypoints(k) for k in frames}
+    flows = {pr: o.read_image_pair_flow(*pr) for pr in o.pairs()}
+    o.close()
+
+    verts, tris = H.bumpy_mesh(clip, quads=8, amp=0.03)
+    mesh = core.AcceleratedMesh(verts, tris)
+    start = H.oracle_cam(clip, first, G.OPENGL)
+    it = start.intrinsics
+    intr = core.CameraIntrinsics(float(it.fx), float(it.fy), float(it.cx), float(it.cy), 1.0, w, h,
+                                 core.CameraConvention.OpenGL)
+    assert intr.fx < 0 and intr.fy < 0
+    scene = core.SceneTransformations(np.eye(4, dtype=F), start.pose.Rt4x4(), intr)
+    bo = core.BundleOptions()
+    bo.loss_type = core.LossType.Cauchy
+
+    # a UI-thread ray cast while the tracker runs must neither deadlock nor wait for the whole sweep
+    stop = threading.Event()
+    hits = []
+
+    def ui_raycasts():
+        while not stop.is_set():
+            hits.append(core.ray_cast(mesh, scene, np.array([w / 2, h / 2], F), True))
+            time.sleep(0.001)
+
+    ui = threading.Thread(target=ui_raycasts)
+    ui.start()
+    results = []
+    try:
+        core.track_sequence(dbp, first, first + NF - 1, scene, mesh, lambda r: results.append(r) or True, False, False, bo)
+    finally:
+        stop.set()
+        ui.join(timeout=60)
+    assert not ui.is_alive() and hits and all(hh is not None for hh in hits)
+    assert [r.frame for r in results] == list(range(first + 1, first + NF))
+    want = otrack.track_sequence(kps, flows, first, first + NF - 1, start, np.eye(4, dtype=F), verts, tris, None,
+                                 opnp.BundleOptions(loss_type=opnp.CAUCHY))
+    for r in results:
+        ocam = want[r.frame][0]
+        dq = np.abs(np.abs(np.array(r.pose.q)) - np.abs(ocam.pose.q)).max()
+        dt = np.abs(np.array(r.pose.t) - ocam.pose.t).max() / np.abs(ocam.pose.t).max()
+        assert dq < 1e-4 and dt < 1e-4, (r.frame, dq, dt)
+        gt = H.oracle_cam(clip, r.frame, G.OPENGL)
+        assert np.abs(np.array(r.pose.t) - gt.pose.t).max() < 5e-3 * clip.depth
+
+    # a callback that returns False stops the sweep after that frame (tracker.cc:178-183)
+    seen = []
+    core.track_sequence(dbp, first, first + NF - 1, scene, mesh, lambda r: seen.append(r.frame) or len(seen) < 3, False,
+                        False, bo)
+    assert seen == [first + 1, first + 2, first + 3]
+
+    traj = core.CameraTrajectory(first, NF)
+    for k in range(first, first + NF):
+        p = core.Pose()
+        if k in (first, first + NF - 1):
+            src = H.oracle_cam(clip, k, G.OPENGL)
+            p.q, p.t = src.pose.q, src.pose.t
+        else:
+            p.q, p.t = results[k - first - 1].pose.q, results[k - first - 1].pose.t
+        traj.set(k, core.CameraState(intr, p))
+    updates = []
+    core.refine_trajectory(dbp, traj, np.eye(4, dtype=F), mesh, False, False, lambda u: updates.append(u) or True, bo)
+    assert updates and updates[-1].stats.cost <= updates[-1].stats.initial_cost
+    for k in range(first + 1, first + NF - 1):
+        gt = H.oracle_cam(clip, k, G.OPENGL)
+        assert np.abs(np.array(traj.get(k).pose.t) - gt.pose.t).max() < 5e-3 * clip.depth
+
+
+def test_resume_with_empty_keypoint_row_is_authoritative(core, tmp_path):
+    """ReadOrGenerateKeypoints (opticalflow.cc:168-178) only detects when the frame has no row: a stored row
+    with zero keypoints stays empty, and no flow row may reference keypoints that are not in the database."""
+    w, h, NF, first = 160, 128, 4, 1
+    clip = synth.Clip(w, h, NF, seed=3, first_frame=first)
+    dbp = str(tmp_path / "resume.db")
+    d = core.Database(dbp)
+    d.write_keypoints(first + 1, np.zeros((0, 2), F))
+    d.close()
+    go = core.GFTTOptions()
+    go.max_corners = 100
+    core.generate_optical_flow_database(core.VideoInfo(w, h, first, NF), lambda f: clip.rgb(f), None, dbp, go)
+    o = odb.Database(dbp)
+    assert len(o.read_keypoints(first + 1)) == 0
+    for (a, b) in o.pairs():
+        idx, tgt, err = o.read_image_pair_flow(a, b)
+        assert len(idx) == 0 if a == first + 1 else idx.max(initial=-1) < len(o.read_keypoints(a))
+    o.close()

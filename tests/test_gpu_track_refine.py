@@ -1,6 +1,16 @@
 """GPU parity tests of the track (K10/K11) and refine (K12-K14) paths through the C ABI,
 against the float32 oracle restatements (oracle/raycast.py, pnp.py, track.py, ba.py).
-Tolerance: 1e-4 relative on poses / costs (BASELINE.json north_star)."""
+
+Every test runs in BOTH camera conventions: OpenCV, and the one the Blender addon actually uses --
+OpenGL with negated fx, fy on bottom-up images (/root/reference/blender_addon/core.py:348-357,
+cpp/pnp/types.h:95-98,129-132,156-170; tests/helpers.py::oracle_cam).
+
+Tolerance: 1e-4 relative on poses / costs / normal equations (BASELINE.json north_star).  The
+comparison value is the oracle with correctly rounded (float64-accumulated) sums -- the value every
+float32 summation order scatters around.  The reference's own sums are order dependent (TBB combines
+thread-local partials in scheduling order, lev_marq.h:231-297,653-771); where a converged LM result
+amplifies that, the oracle is re-run with permuted float32 summation orders and the GPU has to sit
+inside max(1e-4, that noise band)."""
 import numpy as np
 import pytest
 
@@ -8,48 +18,74 @@ from oracle import ba as oba
 from oracle import geometry as G
 from oracle import pnp as opnp
 from oracle import raycast as oray
-from oracle import restate, synth
-from oracle import gftt as ogftt
+from oracle import synth
 from oracle import track as otrack
 from tests import helpers as H
 
 pytestmark = pytest.mark.gpu
 F = np.float32
 RTOL = 1e-4
+CONVENTIONS = [G.OPENCV, G.OPENGL]
+CONV_IDS = ["opencv", "opengl"]
 
 
-@pytest.fixture(scope="module")
-def scene(ctx_small):
-    """12-frame 320x240 clip analysed by the (already parity-tested) GPU analyze path."""
+def analyze_clip(ctx, clip, nf, max_corners, conv, first=0):
+    """Keypoints and flow rows of the clip from the (already parity-tested) GPU analyze path."""
     from polychase_b200 import capi
-    w, h, NF = 320, 240, 12
-    clip = synth.Clip(w, h, NF, seed=4)
-    go = capi.default_gftt(max_corners=250)
     kps, flows = {}, {}
-    ctx_small.analyze_begin(w, h, 0, NF, go)
-    for k in range(NF):
-        ctx_small.analyze_push(k, clip.rgb(k))
-        if ctx_small.analyze_pending() >= 3:
-            r = ctx_small.analyze_pop()
-            kps[r["frame_id"]] = r["keypoints"]
-            for (a, b, rows, idx, tgt, err) in r["pairs"]:
-                flows[(a, b)] = (idx, tgt, err)
-    while ctx_small.analyze_pending():
-        r = ctx_small.analyze_pop()
+    ctx.analyze_begin(clip.width, clip.height, first, nf, capi.default_gftt(max_corners=max_corners))
+
+    def take(r):
         kps[r["frame_id"]] = r["keypoints"]
         for (a, b, rows, idx, tgt, err) in r["pairs"]:
             flows[(a, b)] = (idx, tgt, err)
-    ctx_small.analyze_end()
+
+    for k in range(first, first + nf):
+        ctx.analyze_push(k, H.clip_rgb(clip, k, conv))
+        if ctx.analyze_pending() >= 3:
+            take(ctx.analyze_pop())
+    while ctx.analyze_pending():
+        take(ctx.analyze_pop())
+    ctx.analyze_end()
+    return kps, flows
+
+
+@pytest.fixture(scope="module", params=CONVENTIONS, ids=CONV_IDS)
+def scene(ctx_small, request):
+    """12-frame 320x240 clip seen through the given camera convention."""
+    conv = request.param
+    w, h, NF = 320, 240, 12
+    clip = synth.Clip(w, h, NF, seed=4)
+    kps, flows = analyze_clip(ctx_small, clip, NF, 250, conv)
     verts, tris = H.bumpy_mesh(clip, quads=8, amp=0.03)
-    return dict(clip=clip, kps=kps, flows=flows, verts=verts, tris=tris, NF=NF, w=w, h=h)
+    return dict(clip=clip, kps=kps, flows=flows, verts=verts, tris=tris, NF=NF, w=w, h=h, conv=conv)
 
 
-@pytest.mark.parametrize("convention", [G.OPENCV])
-def test_ray_cast_matches_bruteforce(ctx_small, scene, convention):
-    clip = scene["clip"]
-    cam = H.oracle_cam(clip, 3)
+def cam_of(scene, k):
+    return H.oracle_cam(scene["clip"], k, scene["conv"])
+
+
+def test_scene_cameras_explain_the_flows(scene):
+    """Guards the fixture itself: ray-casting a source keypoint with the source camera and projecting
+    with the target camera lands on the LK target (so the OpenGL variant really is a consistent camera)."""
+    clip, kps, flows = scene["clip"], scene["kps"], scene["flows"]
+    verts, tris = synth.plane_mesh(clip.width, clip.height, clip.s, quads=2)
     model = np.eye(4, dtype=F)
-    model[0, 0] = model[1, 1] = model[2, 2] = 1.0
+    idx, tgt, _ = flows[(3, 4)]
+    a, b = cam_of(scene, 3), cam_of(scene, 4)
+    o, d = oray.ray_object_space(model, a.pose.Rt4x4(), a.intrinsics, kps[3][idx])
+    hit, P, _, _, _ = oray.ray_cast(verts, tris, None, o, d, True)
+    assert hit.mean() > 0.99
+    Pc = b.pose.apply(P[hit])
+    assert not b.intrinsics.is_behind(Pc).any()
+    err = np.linalg.norm(b.intrinsics.project(Pc) - tgt[hit], axis=1)
+    assert np.median(err) < 0.2
+
+
+def test_ray_cast_matches_bruteforce(ctx_small, scene):
+    clip = scene["clip"]
+    cam = cam_of(scene, 3)
+    model = np.eye(4, dtype=F)
     rng = np.random.default_rng(1)
     pos = np.stack([rng.uniform(-20, clip.width + 20, 3000), rng.uniform(-20, clip.height + 20, 3000)], 1).astype(F)
     mask = np.zeros(4, np.uint32)
@@ -58,6 +94,7 @@ def test_ray_cast_matches_bruteforce(ctx_small, scene, convention):
     hit, P, prim, uv, t = ctx_small.ray_cast(model, H.to_abi(cam), pos, True)
     o, d = oray.ray_object_space(model, cam.pose.Rt4x4(), cam.intrinsics, pos)
     eh, eP, eprim, euv, et = oray.ray_cast(scene["verts"], scene["tris"], mask, o, d, True)
+    assert eh.mean() > 0.5                          # the camera does look at the mesh in this convention
     # rays grazing a shared edge may pick either neighbour / flip hit: tolerate a handful
     agree = hit == eh
     assert agree.mean() > 0.998
@@ -69,30 +106,52 @@ def test_ray_cast_matches_bruteforce(ctx_small, scene, convention):
     ctx_small.mesh_set(scene["verts"], scene["tris"])
 
 
+def _pnp_oracle_with_band(X, x, init, opts, opt_f, opt_pp, seeds=(1, 2, 3)):
+    """(exact-sum oracle result, noise band of the float32 summation order)."""
+    with opnp.summation(np.float64):
+        ocam, ost, oinl = opnp.solve_pnp_iterative(X, x, None, init, opts, 12.0, opt_f, opt_pp)
+    bq = bt = bc = bf = 0.0
+    for s in seeds:
+        with opnp.summation(F, perm_seed=s):
+            c, st, _ = opnp.solve_pnp_iterative(X, x, None, init, opts, 12.0, opt_f, opt_pp)
+        dq, dt = H.pose_close(ocam, c)
+        bq, bt = max(bq, dq), max(bt, dt)
+        bc = max(bc, abs(float(st.cost) - float(ost.cost)) / abs(float(ost.cost)))
+        bf = max(bf, abs(float(c.intrinsics.fy) - float(ocam.intrinsics.fy)) / abs(float(ocam.intrinsics.fy)))
+    return ocam, ost, oinl, dict(q=bq, t=bt, cost=bc, f=bf)
+
+
 @pytest.mark.parametrize("loss,opt_f,opt_pp", [(0, False, False), (1, False, False), (2, False, False),
                                                (2, True, False), (2, True, True)])
 def test_solve_pnp_matches_oracle(ctx_small, scene, loss, opt_f, opt_pp):
     from polychase_b200 import capi
     clip = scene["clip"]
-    gt = H.oracle_cam(clip, 5)
+    gt = cam_of(scene, 5)
     rng = np.random.default_rng(7)
     n = 1500
     X = np.stack([rng.uniform(-1.5, 1.5, n), rng.uniform(-1.0, 1.0, n), rng.uniform(-0.05, 0.05, n)], 1).astype(F)
+    assert not gt.intrinsics.is_behind(gt.pose.apply(X)).any()
     x = gt.intrinsics.project(gt.pose.apply(X)) + rng.normal(0, 0.3, (n, 2)).astype(F)
     x[:40] += rng.normal(0, 25, (40, 2)).astype(F)            # outliers
     init = H.perturb(gt, rng)
     opts = opnp.BundleOptions(loss_type=loss)
-    ocam, ost, oinl = opnp.solve_pnp_iterative(X, x, None, init, opts, 12.0, opt_f, opt_pp)
+    ocam, ost, oinl, band = _pnp_oracle_with_band(X, x, init, opts, opt_f, opt_pp)
     gcam, gst, ginl = ctx_small.solve_pnp(X, x, H.to_abi(init), capi.default_bundle(loss_type=loss), None, 12.0,
                                           opt_f, opt_pp)
     g = H.from_abi(gcam)
+    assert int(g.intrinsics.convention) == scene["conv"]
     dq, dt = H.pose_close(ocam, g)
-    assert dq < RTOL and dt < RTOL, (dq, dt)
-    assert abs(gst.cost - ost.cost) <= 1e-3 * abs(ost.cost)
+    assert dq <= max(RTOL, band["q"]) and dt <= max(RTOL, band["t"]), (dq, dt, band)
+    assert abs(gst.cost - ost.cost) <= max(RTOL, band["cost"]) * abs(ost.cost), (gst.cost, ost.cost, band)
     assert abs(gst.initial_cost - ost.initial_cost) <= RTOL * abs(ost.initial_cost)
     assert abs(ginl - oinl) < 2e-3
-    assert abs(g.intrinsics.fy - ocam.intrinsics.fy) <= RTOL * abs(ocam.intrinsics.fy)
+    assert abs(g.intrinsics.fy - ocam.intrinsics.fy) <= max(RTOL, band["f"]) * abs(ocam.intrinsics.fy)
     assert abs(g.intrinsics.cx - ocam.intrinsics.cx) <= RTOL * abs(ocam.intrinsics.cx) + 1e-3
+    if opt_f:                                                 # the focal length moved, and stayed inside the convention's bounds
+        b = init.intrinsics.bounds()
+        assert b["f_low"] <= g.intrinsics.fy <= b["f_high"] and b["f_low"] < b["f_high"]
+        assert (g.intrinsics.fy < 0) == (scene["conv"] == G.OPENGL)
+        assert g.intrinsics.fx == F(g.intrinsics.fy * g.intrinsics.aspect_ratio)
 
 
 def test_solve_pnp_errors(ctx_small):
@@ -105,6 +164,24 @@ def test_solve_pnp_errors(ctx_small):
         ctx_small.solve_pnp(np.zeros((5, 3), F), np.zeros((5, 2), F), cam, capi.default_bundle(loss_type=7))
 
 
+def _track_oracle_with_band(scene, opts, opt_f=False, seeds=(1, 2)):
+    clip, kps, flows, NF = scene["clip"], scene["kps"], scene["flows"], scene["NF"]
+    model = np.eye(4, dtype=F)
+    start = cam_of(scene, 0)
+    args = (kps, flows, 0, NF - 1, start, model, scene["verts"], scene["tris"], None, opts, opt_f, False)
+    with opnp.summation(np.float64):
+        want = otrack.track_sequence(*args)
+    band = {f: [0.0, 0.0, 0.0] for f in want}
+    for s in seeds:
+        with opnp.summation(F, perm_seed=s):
+            alt = otrack.track_sequence(*args)
+        for f in want:
+            dq, dt = H.pose_close(want[f][0], alt[f][0])
+            df = abs(float(alt[f][0].intrinsics.fy) - float(want[f][0].intrinsics.fy)) / abs(float(want[f][0].intrinsics.fy))
+            band[f] = [max(band[f][0], dq), max(band[f][1], dt), max(band[f][2], df)]
+    return want, band
+
+
 def test_track_sequence_matches_oracle(ctx_small, scene):
     """SolveFrame chained over the clip (tracker.cc:133-192): GPU poses vs the oracle's."""
     from polychase_b200 import capi
@@ -112,9 +189,8 @@ def test_track_sequence_matches_oracle(ctx_small, scene):
     model = np.eye(4, dtype=F)
     ctx_small.mesh_set(scene["verts"], scene["tris"])
     opts = opnp.BundleOptions(loss_type=opnp.CAUCHY)
-    start = H.oracle_cam(clip, 0)
-    want = otrack.track_sequence(kps, flows, 0, NF - 1, start, model, scene["verts"], scene["tris"], None, opts)
-    traj = {0: H.to_abi(start)}
+    want, band = _track_oracle_with_band(scene, opts)
+    traj = {0: H.to_abi(cam_of(scene, 0))}
     bo = capi.default_bundle(loss_type=2)
     for f in range(1, NF):
         srcs = []
@@ -125,12 +201,13 @@ def test_track_sequence_matches_oracle(ctx_small, scene):
         cam, st, inl, m = ctx_small.track_frame(srcs, model, traj[f - 1], bo)
         traj[f] = cam
         ocam, ost, oinl, om = want[f]
+        assert om > 200
         assert abs(m - om) <= max(2, 0.002 * om)
         dq, dt = H.pose_close(ocam, H.from_abi(cam))
-        assert dq < RTOL and dt < RTOL, (f, dq, dt)
+        assert dq <= max(RTOL, band[f][0]) and dt <= max(RTOL, band[f][1]), (f, dq, dt, band[f])
         assert abs(inl - oinl) < 5e-3
     # and the ground truth is recovered
-    dq, dt = H.pose_close(H.oracle_cam(clip, NF - 1), H.from_abi(traj[NF - 1]))
+    dq, dt = H.pose_close(cam_of(scene, NF - 1), H.from_abi(traj[NF - 1]))
     assert dq < 2e-3 and dt < 2e-3
 
 
@@ -142,9 +219,8 @@ def test_fused_analyze_track_chain_matches_oracle(ctx_small, scene, opt_f):
     clip, kps, flows, NF = scene["clip"], scene["kps"], scene["flows"], scene["NF"]
     model = np.eye(4, dtype=F)
     opts = opnp.BundleOptions(loss_type=opnp.CAUCHY)
-    start = H.oracle_cam(clip, 0)
-    want = otrack.track_sequence(kps, flows, 0, NF - 1, start, model, scene["verts"], scene["tris"], None, opts,
-                                 opt_f, False)
+    start = cam_of(scene, 0)
+    want, band = _track_oracle_with_band(scene, opts, opt_f)
     ctx_small.mesh_set(scene["verts"], scene["tris"])
     ctx_small.analyze_begin(clip.width, clip.height, 0, NF, capi.default_gftt(max_corners=250))
     ctx_small.analyze_track_begin(model, capi.default_bundle(loss_type=2), opt_f, False)
@@ -158,7 +234,7 @@ def test_fused_analyze_track_chain_matches_oracle(ctx_small, scene, opt_f):
             assert np.array_equal(idx, flows[(a, b)][0]) and np.array_equal(tgt, flows[(a, b)][1])
 
     for k in range(NF):
-        ctx_small.analyze_push(k, clip.rgb(k))
+        ctx_small.analyze_push(k, H.clip_rgb(clip, k, scene["conv"]))
         if ctx_small.analyze_pending() >= 3:
             take(ctx_small.analyze_pop())
     while ctx_small.analyze_pending():
@@ -172,13 +248,12 @@ def test_fused_analyze_track_chain_matches_oracle(ctx_small, scene, opt_f):
         assert abs(r["num_matches"] - om) <= max(2, 0.002 * om)
         g = H.from_abi(r["camera"])
         dq, dt = H.pose_close(ocam, g)
-        # with the focal length free, depth and focal length trade off along a nearly flat valley on
-        # this almost planar scene (and the chain feeds each pose to the next frame): the rotation
-        # still agrees to 1e-4, translation / focal length to 1e-3
-        tol = 10 * RTOL if opt_f else RTOL
-        assert dq < RTOL and dt < tol, (f, dq, dt)
+        # with the focal length free, depth and focal length trade off along a nearly flat valley on this
+        # almost planar scene and the chain feeds each pose to the next frame: the reference's own
+        # summation-order noise (band) is what bounds the agreement there
+        assert dq <= max(RTOL, band[f][0]) and dt <= max(RTOL, band[f][1]), (f, dq, dt, band[f])
         assert abs(r["inlier_ratio"] - oinl) < 5e-3
-        assert abs(g.intrinsics.fy - ocam.intrinsics.fy) <= tol * abs(ocam.intrinsics.fy)
+        assert abs(g.intrinsics.fy - ocam.intrinsics.fy) <= max(RTOL, band[f][2]) * abs(ocam.intrinsics.fy)
 
 
 def test_fused_chain_not_enough_features(ctx_small, scene):
@@ -190,9 +265,9 @@ def test_fused_chain_not_enough_features(ctx_small, scene):
     ctx_small.mesh_set(far, scene["tris"])
     ctx_small.analyze_begin(clip.width, clip.height, 0, NF, capi.default_gftt(max_corners=250))
     ctx_small.analyze_track_begin(np.eye(4, dtype=F), capi.default_bundle())
-    ctx_small.analyze_track_seed(0, H.to_abi(H.oracle_cam(clip, 0)))
-    ctx_small.analyze_push(0, clip.rgb(0))
-    ctx_small.analyze_push(1, clip.rgb(1))
+    ctx_small.analyze_track_seed(0, H.to_abi(cam_of(scene, 0)))
+    ctx_small.analyze_push(0, H.clip_rgb(clip, 0, scene["conv"]))
+    ctx_small.analyze_push(1, H.clip_rgb(clip, 1, scene["conv"]))
     assert ctx_small.analyze_pop()["tracked"] == 2
     with pytest.raises(capi.PcError) as e:
         ctx_small.analyze_pop()
@@ -204,70 +279,127 @@ def test_fused_chain_not_enough_features(ctx_small, scene):
 def test_track_not_enough_features(ctx_small, scene):
     from polychase_b200 import capi
     ctx_small.mesh_set(scene["verts"], scene["tris"])
-    cam = H.to_abi(H.oracle_cam(scene["clip"], 0))
+    cam = H.to_abi(cam_of(scene, 0))
     with pytest.raises(capi.PcError) as e:
         ctx_small.track_frame([(cam, np.zeros((2, 2), F), np.array([0, 1], np.uint32), np.zeros((2, 2), F))],
                               np.eye(4, dtype=F), cam)
     assert e.value.code == -7
 
 
-def _ba_setup(scene, rng, opt_f=False, opt_pp=False, perturb=True):
-    clip, kps, flows, NF = scene["clip"], scene["kps"], scene["flows"], scene["NF"]
+def ba_setup(scene, rng, opt_f=False, opt_pp=False, perturb=True, rot_deg=0.05, trans=0.004):
+    kps, flows, NF = scene["kps"], scene["flows"], scene["NF"]
+    first = scene.get("first", 0)
     model = np.eye(4, dtype=F)
-    traj = [H.oracle_cam(clip, k) for k in range(NF)]
+    traj = [cam_of(scene, first + k) for k in range(NF)]
     if perturb:
         for k in range(1, NF - 1):
-            traj[k] = H.perturb(traj[k], rng, rot_deg=0.05, trans=0.004)
-    edges = [oba.Edge(a, b, flows[(a, b)][0], flows[(a, b)][1]) for (a, b) in sorted(flows) if len(flows[(a, b)][0])]
-    prob = oba.RefineProblem([kps[k] for k in range(NF)], edges, scene["verts"], scene["tris"], None, model,
+            traj[k] = H.perturb(traj[k], rng, rot_deg=rot_deg, trans=trans)
+    edges = [oba.Edge(a - first, b - first, flows[(a, b)][0], flows[(a, b)][1]) for (a, b) in sorted(flows)
+             if len(flows[(a, b)][0])]
+    prob = oba.RefineProblem([kps[first + k] for k in range(NF)], edges, scene["verts"], scene["tris"], None, model,
                              opt_f, opt_pp, traj[0].intrinsics.bounds())
     abi_edges = [(e.src, e.tgt, e.src_kps_indices, e.tgt_kps) for e in edges]
     return model, traj, prob, abi_edges
 
 
-@pytest.mark.parametrize("opt_f,opt_pp,loss", [(False, False, 2), (True, True, 2), (False, False, 1)])
-def test_ba_cost_and_normal_equations(ctx_small, scene, opt_f, opt_pp, loss):
+def check_cost_and_normal_equations(ctx, scene, opt_f, opt_pp, loss, seed=3):
     from polychase_b200 import capi
-    rng = np.random.default_rng(3)
-    model, traj, prob, abi_edges = _ba_setup(scene, rng, opt_f, opt_pp)
-    ctx_small.mesh_set(scene["verts"], scene["tris"])
-    ctx_small.ba_load([scene["kps"][k] for k in range(scene["NF"])], abi_edges, model, opt_f, opt_pp)
+    rng = np.random.default_rng(seed)
+    model, traj, prob, abi_edges = ba_setup(scene, rng, opt_f, opt_pp)
+    first = scene.get("first", 0)
+    ctx.mesh_set(scene["verts"], scene["tris"])
+    ctx.ba_load([scene["kps"][first + k] for k in range(scene["NF"])], abi_edges, model, opt_f, opt_pp)
     bo = capi.default_bundle(loss_type=loss)
     lo = opnp.Loss(loss, 1.0)
     atraj = [H.to_abi(c) for c in traj]
-    want_cost = prob.total_cost(traj, lo)
-    got_cost = ctx_small.ba_cost(atraj, bo)
-    assert abs(got_cost - want_cost) <= 2e-4 * abs(want_cost)
-    A, g = prob.normal_equations(traj, lo)
-    band, jtr = ctx_small.ba_normal_equations(atraj, bo)
+    with opnp.summation(np.float64):
+        want_cost = prob.total_cost(traj, lo)
+        A, g = prob.normal_equations(traj, lo)
+    got_cost = ctx.ba_cost(atraj, bo)
+    assert abs(got_cost - want_cost) <= RTOL * abs(want_cost), (got_cost, want_cost)
+    # the primitive-id cache the cost pass leaves behind (refiner.cc:323-350) is the oracle's
+    cache = ctx.ba_read_cache(int(prob.offs[-1]))
+    want_cache = np.concatenate(prob.cache)
+    assert (cache == want_cache).mean() > 0.998
+    band, jtr = ctx.ba_normal_equations(atraj, bo)
     Ag = capi.band_to_dense(band)
-    scale = np.abs(A).max()
-    assert np.abs(Ag - np.tril(A)).max() <= 5e-4 * scale
-    assert np.abs(jtr - g).max() <= 5e-4 * np.abs(g).max()
-    # first / last frame are ground truth: their blocks are empty (refiner.cc:611-612)
     p = prob.p
+    # per block: relative to that block's largest entry (a global max would hide the small blocks)
+    nf = prob.nf
+    worst = 0.0
+    for i in range(nf):
+        for j in range(max(0, i - 8), i + 1):
+            blk_w = np.tril(A)[i * p:(i + 1) * p, j * p:(j + 1) * p]
+            blk_g = Ag[i * p:(i + 1) * p, j * p:(j + 1) * p]
+            s = np.abs(blk_w).max()
+            if s == 0:
+                assert not blk_g.any()
+                continue
+            worst = max(worst, float(np.abs(blk_g - blk_w).max() / s))
+    assert worst <= RTOL, worst
+    for i in range(nf):
+        s = np.abs(g[i * p:(i + 1) * p]).max()
+        if s > 0:
+            assert np.abs(jtr[i * p:(i + 1) * p] - g[i * p:(i + 1) * p]).max() <= RTOL * max(s, 1e-3 * np.abs(g).max())
+    # first / last frame are ground truth: their blocks are empty (refiner.cc:611-612)
     assert np.all(Ag[:p, :] == 0) and np.all(Ag[-p:, :] == 0)
+    return prob
+
+
+@pytest.mark.parametrize("opt_f,opt_pp,loss", [(False, False, 2), (True, True, 2), (False, False, 1)])
+def test_ba_cost_and_normal_equations(ctx_small, scene, opt_f, opt_pp, loss):
+    check_cost_and_normal_equations(ctx_small, scene, opt_f, opt_pp, loss)
+
+
+def ba_oracle_with_band(scene, seed, opt_f, opt_pp, iters, seeds=(1, 2), **setup_kw):
+    """Exact-sum oracle refine + the noise band of permuted float32 summation orders."""
+    opts = opnp.BundleOptions(loss_type=opnp.CAUCHY, max_iterations=iters)
+    model, traj, prob, abi_edges = ba_setup(scene, np.random.default_rng(seed), opt_f, opt_pp, **setup_kw)
+    with opnp.summation(np.float64):
+        want, wst = oba.refine_trajectory(prob, traj, opts)
+    bq = bt = bc = 0.0
+    for s in seeds:
+        _, traj2, prob2, _ = ba_setup(scene, np.random.default_rng(seed), opt_f, opt_pp, **setup_kw)
+        with opnp.summation(F, perm_seed=s):
+            alt, ast = oba.refine_trajectory(prob2, traj2, opts)
+        for k in range(len(traj)):
+            dq, dt = H.pose_close(want[k], alt[k])
+            bq, bt = max(bq, dq), max(bt, dt)
+        bc = max(bc, abs(float(ast.cost) - float(wst.cost)) / abs(float(wst.cost)))
+    return model, traj, abi_edges, want, wst, dict(q=bq, t=bt, cost=bc)
 
 
 @pytest.mark.parametrize("opt_f,opt_pp", [(False, False), (True, False)])
 def test_ba_solve_matches_oracle(ctx_small, scene, opt_f, opt_pp):
     from polychase_b200 import capi
-    rng = np.random.default_rng(5)
-    model, traj, prob, abi_edges = _ba_setup(scene, rng, opt_f, opt_pp)
+    model, traj, abi_edges, want, wst, band = ba_oracle_with_band(scene, 5, opt_f, opt_pp, 30)
     ctx_small.mesh_set(scene["verts"], scene["tris"])
     ctx_small.ba_load([scene["kps"][k] for k in range(scene["NF"])], abi_edges, model, opt_f, opt_pp)
-    opts = opnp.BundleOptions(loss_type=opnp.CAUCHY, max_iterations=30)
-    want, wst = oba.refine_trajectory(prob, traj, opts)
     seen = []
     got, gst = ctx_small.ba_solve([H.to_abi(c) for c in traj], capi.default_bundle(loss_type=2, max_iterations=30),
                                   callback=lambda s: seen.append(s.cost) or True)
     assert len(seen) >= 1
-    assert abs(gst.initial_cost - wst.initial_cost) <= 2e-4 * abs(wst.initial_cost)
+    assert abs(gst.initial_cost - wst.initial_cost) <= RTOL * abs(wst.initial_cost)
     assert gst.cost <= gst.initial_cost
-    assert abs(gst.cost - wst.cost) <= 2e-3 * abs(wst.cost)
+    assert abs(gst.cost - wst.cost) <= max(RTOL, band["cost"]) * abs(wst.cost), (gst.cost, wst.cost, band)
     for k in range(len(traj)):
         dq, dt = H.pose_close(want[k], H.from_abi(got[k]))
-        assert dq < 2e-4 and dt < 2e-4, (k, dq, dt)
+        assert dq <= max(RTOL, band["q"]) and dt <= max(RTOL, band["t"]), (k, dq, dt, band)
+        assert int(got[k].convention) == scene["conv"]
     # end frames untouched
     for k in (0, len(traj) - 1):
         assert list(got[k].q) == [float(v) for v in traj[k].pose.q]
+
+
+def test_ba_empty_problem_returns_trajectory_unchanged(ctx_small, scene):
+    """No keypoint inside the projected mesh bbox -> no edges, no residuals: RefineTrajectory leaves the
+    trajectory as it is (refiner.cc:649-725 with an empty CachedDatabase) instead of failing a launch."""
+    from polychase_b200 import capi
+    NF = 4
+    traj = [H.to_abi(cam_of(scene, k)) for k in range(NF)]
+    ctx_small.mesh_set(scene["verts"], scene["tris"])
+    ctx_small.ba_load([np.zeros((0, 2), F) for _ in range(NF)], [], np.eye(4, dtype=F), False, False)
+    assert ctx_small.ba_cost(traj, capi.default_bundle(loss_type=2)) == 0.0
+    got, st = ctx_small.ba_solve(traj, capi.default_bundle(loss_type=2, max_iterations=5))
+    for k in range(NF):
+        assert list(got[k].q) == list(traj[k].q) and list(got[k].t) == list(traj[k].t)
