@@ -239,8 +239,9 @@ PC_API int pc_memcpy_h2d(pc_ctx*, void* dst, const void* src, size_t bytes);
 /* Per-kernel-family device time accumulated since the last reset, in ms (CUDA events on
  * the launching stream; only collected after pc_timing_enable(ctx,1)). */
 typedef struct pc_kernel_times {
-    double gray_pyr_ms, min_eig_ms, select_ms, lk_ms, compact_ms, raycast_ms, pnp_ms, ba_ms;
-    uint64_t gray_pyr_n, min_eig_n, select_n, lk_n, compact_n, raycast_n, pnp_n, ba_n;
+    /* lk = the 8-pair LK batch launches only; lk_tmpl = the once-per-frame source template launches */
+    double gray_pyr_ms, min_eig_ms, select_ms, lk_ms, compact_ms, raycast_ms, pnp_ms, ba_ms, lk_tmpl_ms;
+    uint64_t gray_pyr_n, min_eig_n, select_n, lk_n, compact_n, raycast_n, pnp_n, ba_n, lk_tmpl_n;
 } pc_kernel_times;
 PC_API int pc_timing_enable(pc_ctx*, int on);
 /* Whole-region device timing: pc_mark joins the context's three streams and records CUDA

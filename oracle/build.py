@@ -13,7 +13,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 OUT_DIR = os.path.join(HERE, "_build")
 LIB = os.path.join(OUT_DIR, "liboracle_restate.so")
-SRC = [os.path.join(HERE, "restate.c")]
+SRC = [os.path.join(HERE, "restate.c"), os.path.join(HERE, "track_port.c")]
 
 
 def build(force: bool = False) -> str:

@@ -82,9 +82,9 @@ class FrameResult(C.Structure):
 
 class KernelTimes(C.Structure):
     _fields_ = [(n, C.c_double) for n in ("gray_pyr_ms", "min_eig_ms", "select_ms", "lk_ms", "compact_ms",
-                                           "raycast_ms", "pnp_ms", "ba_ms")] + \
+                                           "raycast_ms", "pnp_ms", "ba_ms", "lk_tmpl_ms")] + \
                [(n, C.c_uint64) for n in ("gray_pyr_n", "min_eig_n", "select_n", "lk_n", "compact_n",
-                                           "raycast_n", "pnp_n", "ba_n")]
+                                           "raycast_n", "pnp_n", "ba_n", "lk_tmpl_n")]
 
 
 class MatchSource(C.Structure):

@@ -821,7 +821,7 @@ static int enqueue_lk(pc_ctx* c, Stage& st, FrameSlot* f) {
     int rc;
     // source templates of this frame's keypoints (once per frame; its eight pairs load them)
     if (f->tmpl && lkp.win == 10 && lkp.max_level + 1 <= f->tmpl_levels) {
-        span_begin(c, KF_LK, lks);
+        span_begin(c, KF_LK_TMPL, lks);
         launch_lk10_templates(view_of(*f), f->kps, f->n_kps, c->lim.max_features, lkp, f->tmpl, f->tmpl_sums, lks);
         span_end(c, lks);
         rc = check_launch(c, "lk templates", 1);
@@ -1105,6 +1105,7 @@ int pc_timing_read(pc_ctx* c, pc_kernel_times* out, int reset) {
         out->raycast_ms = c->fam_ms[KF_RAYCAST]; out->raycast_n = c->fam_n[KF_RAYCAST];
         out->pnp_ms = c->fam_ms[KF_PNP]; out->pnp_n = c->fam_n[KF_PNP];
         out->ba_ms = c->fam_ms[KF_BA]; out->ba_n = c->fam_n[KF_BA];
+        out->lk_tmpl_ms = c->fam_ms[KF_LK_TMPL]; out->lk_tmpl_n = c->fam_n[KF_LK_TMPL];
     }
     if (reset) {
         for (int i = 0; i < KF_COUNT; i++) { c->fam_ms[i] = 0; c->fam_n[i] = 0; }

@@ -35,7 +35,7 @@ struct FrameSlot {
     bool has_tmpl = false;        // computed for the frame and keypoints the slot holds now
 };
 
-enum KernelFamily { KF_GRAY_PYR = 0, KF_MIN_EIG, KF_SELECT, KF_LK, KF_COMPACT, KF_RAYCAST, KF_PNP, KF_BA, KF_COUNT };
+enum KernelFamily { KF_GRAY_PYR = 0, KF_MIN_EIG, KF_SELECT, KF_LK, KF_COMPACT, KF_RAYCAST, KF_PNP, KF_BA, KF_LK_TMPL, KF_COUNT };
 
 struct TimedSpan {
     int family;

@@ -10,7 +10,8 @@ comparison value is the oracle with correctly rounded (float64-accumulated) sums
 float32 summation order scatters around.  The reference's own sums are order dependent (TBB combines
 thread-local partials in scheduling order, lev_marq.h:231-297,653-771); where a converged LM result
 amplifies that, the oracle is re-run with permuted float32 summation orders and the GPU has to sit
-inside max(1e-4, that noise band)."""
+inside max(1e-4, BAND x the largest deviation those few samples show) -- BAND = 2 because the maximum
+of two or three samples underestimates the spread of the distribution they are drawn from."""
 import numpy as np
 import pytest
 
@@ -25,6 +26,7 @@ from tests import helpers as H
 pytestmark = pytest.mark.gpu
 F = np.float32
 RTOL = 1e-4
+BAND = 2.0
 CONVENTIONS = [G.OPENCV, G.OPENGL]
 CONV_IDS = ["opencv", "opengl"]
 
@@ -118,7 +120,7 @@ def _pnp_oracle_with_band(X, x, init, opts, opt_f, opt_pp, seeds=(1, 2, 3)):
         bq, bt = max(bq, dq), max(bt, dt)
         bc = max(bc, abs(float(st.cost) - float(ost.cost)) / abs(float(ost.cost)))
         bf = max(bf, abs(float(c.intrinsics.fy) - float(ocam.intrinsics.fy)) / abs(float(ocam.intrinsics.fy)))
-    return ocam, ost, oinl, dict(q=bq, t=bt, cost=bc, f=bf)
+    return ocam, ost, oinl, dict(q=BAND * bq, t=BAND * bt, cost=BAND * bc, f=BAND * bf)
 
 
 @pytest.mark.parametrize("loss,opt_f,opt_pp", [(0, False, False), (1, False, False), (2, False, False),
@@ -164,7 +166,7 @@ def test_solve_pnp_errors(ctx_small):
         ctx_small.solve_pnp(np.zeros((5, 3), F), np.zeros((5, 2), F), cam, capi.default_bundle(loss_type=7))
 
 
-def _track_oracle_with_band(scene, opts, opt_f=False, seeds=(1, 2)):
+def _track_oracle_with_band(scene, opts, opt_f=False, seeds=(1, 2, 3)):
     clip, kps, flows, NF = scene["clip"], scene["kps"], scene["flows"], scene["NF"]
     model = np.eye(4, dtype=F)
     start = cam_of(scene, 0)
@@ -178,7 +180,7 @@ def _track_oracle_with_band(scene, opts, opt_f=False, seeds=(1, 2)):
         for f in want:
             dq, dt = H.pose_close(want[f][0], alt[f][0])
             df = abs(float(alt[f][0].intrinsics.fy) - float(want[f][0].intrinsics.fy)) / abs(float(want[f][0].intrinsics.fy))
-            band[f] = [max(band[f][0], dq), max(band[f][1], dt), max(band[f][2], df)]
+            band[f] = [max(band[f][0], BAND * dq), max(band[f][1], BAND * dt), max(band[f][2], BAND * df)]
     return want, band
 
 
@@ -366,7 +368,7 @@ def ba_oracle_with_band(scene, seed, opt_f, opt_pp, iters, seeds=(1, 2), **setup
             dq, dt = H.pose_close(want[k], alt[k])
             bq, bt = max(bq, dq), max(bt, dt)
         bc = max(bc, abs(float(ast.cost) - float(wst.cost)) / abs(float(wst.cost)))
-    return model, traj, abi_edges, want, wst, dict(q=bq, t=bt, cost=bc)
+    return model, traj, abi_edges, want, wst, dict(q=BAND * bq, t=BAND * bt, cost=BAND * bc)
 
 
 @pytest.mark.parametrize("opt_f,opt_pp", [(False, False), (True, False)])
