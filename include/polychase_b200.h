@@ -310,10 +310,31 @@ PC_API int pc_ba_normal_equations(pc_ctx*, const pc_camera_state* traj, const pc
 /* The per-(frame, keypoint) primitive-id cache of RefinementProblemBase (refiner.cc:235-242,
  * 547-559), in the order of pc_ba_problem.keypoints; 0xFFFFFFFF = no intersection cached. */
 PC_API int pc_ba_read_cache(pc_ctx*, uint32_t* out, int cap);
+/* ComputeStep (lev_marq.h:826-841) on the normal equations the last pc_ba_normal_equations left on the device:
+ * step = -(JtJ with diag * (1 + lambda))^-1 Jtr through the block-banded Cholesky kernel (K14).  step_out:
+ * num_frames * p floats (p = 6, or 9 with intrinsics); PC_ERR_STATE when a pivot is not positive. */
+PC_API int pc_ba_solve_step(pc_ctx*, float lambda, float* step_out, float* step_norm_out);
 typedef int (*pc_ba_iter_cb)(const pc_bundle_stats*, void* user);
 /* LevMarqSparseSolve over the loaded problem, lev_marq.h:492-588; traj is in/out. */
 PC_API int pc_ba_solve(pc_ctx*, const pc_bundle_opts*, pc_camera_state* traj, pc_bundle_stats* stats,
                        pc_ba_iter_cb cb, void* user);
+
+/* ---- multi-GPU: one process per GPU, NCCL over NVLink -------------------------
+ * Rank 0 makes the id, the launcher carries its bytes to the other ranks, every rank joins with its context.
+ * libnccl.so.2 is opened at run time; without it these calls fail with PC_ERR_STATE. */
+#define PC_COMM_ID_BYTES 128
+PC_API int pc_comm_unique_id(uint8_t id_out[PC_COMM_ID_BYTES]);
+PC_API int pc_comm_init(pc_ctx*, int world, int rank, const uint8_t id[PC_COMM_ID_BYTES]);
+PC_API int pc_comm_destroy(pc_ctx*);
+/* The path's one collective: stitches per-GPU trajectory segments before the global refine (the addon's segment
+ * notion, blender_addon/operators/tracking.py:103-109; TrackSequence per segment, tracker.cc:194-213).  `local`:
+ * this rank's n_local records; counts[world]: every rank's segment length; `all`: sum(counts) records in rank order. */
+PC_API int pc_traj_allgather(pc_ctx*, const pc_camera_state* local, int n_local, const int* counts, pc_camera_state* all);
+/* Edge-sharded refine: after pc_comm_init + pc_ba_load (in that order) every rank evaluates a contiguous share of
+ * the edges (BuildNormalEquations / TotalCost, lev_marq.h:653-824); the per-edge blocks and costs are all-gathered
+ * once per LM iteration each and every rank then assembles, factors and decides identically.  The result equals the
+ * single-GPU pc_ba_solve bit for bit. */
+PC_API int pc_ba_set_edge_shard(pc_ctx*, int on);
 
 #ifdef __cplusplus
 }

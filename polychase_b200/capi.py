@@ -158,6 +158,12 @@ SIGNATURES = {
     "pc_ba_normal_equations": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(BundleOpts), C.c_void_p, C.c_void_p]),
     "pc_ba_read_cache": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "pc_ba_solve": (C.c_int, [C.c_void_p, C.POINTER(BundleOpts), C.c_void_p, C.POINTER(BundleStats), BA_ITER_CB, C.c_void_p]),
+    "pc_ba_solve_step": (C.c_int, [C.c_void_p, C.c_float, C.c_void_p, C.POINTER(C.c_float)]),
+    "pc_comm_unique_id": (C.c_int, [C.c_void_p]),
+    "pc_comm_init": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "pc_comm_destroy": (C.c_int, [C.c_void_p]),
+    "pc_traj_allgather": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "pc_ba_set_edge_shard": (C.c_int, [C.c_void_p, C.c_int]),
 }
 
 
@@ -602,7 +608,55 @@ def band_to_dense(band: np.ndarray) -> np.ndarray:
     return A
 
 
+def _ctx_ba_solve_step(self, lam: float):
+    """step = -(A with diag * (1 + lam))^-1 Jtr of the last ba_normal_equations (K14 on its own)."""
+    out = np.zeros(self._ba_nf * self._ba_p, np.float32)
+    sn = C.c_float()
+    self._chk(self.lib.pc_ba_solve_step(self.h, float(lam), _ptr(out), C.byref(sn)))
+    return out, float(sn.value)
+
+
+COMM_ID_BYTES = 128
+
+
+def comm_unique_id() -> bytes:
+    """ncclGetUniqueId through the C ABI (rank 0); carry the bytes to the other ranks."""
+    buf = (C.c_uint8 * COMM_ID_BYTES)()
+    rc = load().pc_comm_unique_id(buf)
+    if rc != 0:
+        raise PcError(rc, load().pc_last_error(None).decode())
+    return bytes(buf)
+
+
+def _ctx_comm_init(self, world: int, rank: int, uid: bytes):
+    buf = (C.c_uint8 * COMM_ID_BYTES).from_buffer_copy(uid)
+    self._chk(self.lib.pc_comm_init(self.h, world, rank, buf))
+    self._comm = (world, rank)
+
+
+def _ctx_comm_destroy(self):
+    self._chk(self.lib.pc_comm_destroy(self.h))
+
+
+def _ctx_traj_allgather(self, local, counts):
+    """local: list of CameraState (this rank's segment); counts: every rank's segment length."""
+    arr = _traj_array(local) if len(local) else (CameraState * 1)()
+    cnt = (C.c_int * len(counts))(*[int(x) for x in counts])
+    out = (CameraState * max(int(sum(counts)), 1))()
+    self._chk(self.lib.pc_traj_allgather(self.h, arr, len(local), cnt, out))
+    return [CameraState.from_buffer_copy(out[i]) for i in range(int(sum(counts)))]
+
+
+def _ctx_ba_set_edge_shard(self, on: bool = True):
+    self._chk(self.lib.pc_ba_set_edge_shard(self.h, 1 if on else 0))
+
+
 Context.mesh_set = _ctx_mesh_set
+Context.ba_solve_step = _ctx_ba_solve_step
+Context.comm_init = _ctx_comm_init
+Context.comm_destroy = _ctx_comm_destroy
+Context.traj_allgather = _ctx_traj_allgather
+Context.ba_set_edge_shard = _ctx_ba_set_edge_shard
 Context.ray_cast = _ctx_ray_cast
 Context.solve_pnp = _ctx_solve_pnp
 Context.track_frame = _ctx_track_frame

@@ -1,6 +1,14 @@
 // C ABI: trajectory refinement (bundle adjustment) -- problem upload, cost, normal equations and
 // the sparse Levenberg-Marquardt loop (RefineTrajectory / LevMarqSparseSolve,
 // /root/reference/cpp/refiner.cc:649-690, /root/reference/cpp/pnp/lev_marq.h:492-588).
+//
+// The LM loop runs on the device (kernels/ba_lm.cu): parameters, candidate parameters and the loop state
+// stay in HBM, the host enqueues one fixed launch sequence per iteration and synchronises once per
+// callback.  Edge-sharded refine: with pc_ba_set_edge_shard every rank evaluates a
+// contiguous share of the edges; the per-edge normal-equation blocks and the per-edge costs are
+// all-gathered (NCCL, comm.cu) once per iteration each, after which every rank assembles, factors and
+// decides identically -- bit-equal to the single-GPU solve, because every gathered value was produced by
+// exactly one rank and the assembly order does not change.
 #include <math.h>
 #include <string.h>
 
@@ -8,6 +16,7 @@
 #include <vector>
 
 #include "../kernels/ba_kernels.h"
+#include "comm.h"
 #include "context.h"
 #include "mesh.h"
 
@@ -16,15 +25,26 @@ namespace pc {
 struct BAData {
     BAView v{};
     std::vector<void*> allocs;
-    std::vector<pc_camera_state> host_traj;
-    pc_camera_state* d_cams = nullptr;
-    float* d_scalars = nullptr;
+    pc_camera_state* d_cams = nullptr;        // current parameters
+    pc_camera_state* d_cams_new = nullptr;    // candidate parameters of the iteration
+    float* d_scalars = nullptr;               // [0] cost [1] grad_norm [2] step_norm [4] llt_ok [5] cost_new
+    float* d_expected = nullptr;              // nf partial sums of the expected cost change
+    BALmState* d_state = nullptr;
+    BALmState* h_state = nullptr;             // pinned mirror
+    pc_camera_state* h_cams = nullptr;        // pinned staging of the trajectory
+    uint8_t* d_edge_mask = nullptr;
     int opt_f = 0, opt_pp = 0;
+    // edge sharding
+    bool sharded = false;
+    int edges_per_rank = 0;                   // chunk size of the all-gathers (the arrays are padded to world * chunk)
+    int n_edges_padded = 0;
 };
 
 void free_ba(BAData* b) {
     if (!b) return;
     for (void* p : b->allocs) cudaFree(p);
+    cudaFreeHost(b->h_state);
+    cudaFreeHost(b->h_cams);
     delete b;
 }
 
@@ -47,43 +67,52 @@ static int dev_upload(pc_ctx* c, BAData* b, const T** out, const T* host, size_t
     return PC_OK;
 }
 
-static int upload_traj(pc_ctx* c, BAData* b, const pc_camera_state* traj) {
-    PC_CUDA(c, cudaMemcpyAsync(b->d_cams, traj, sizeof(pc_camera_state) * b->v.nf, cudaMemcpyHostToDevice, c->compute));
+static int upload_traj(pc_ctx* c, BAData* b, const pc_camera_state* traj, pc_camera_state* dst) {
+    memcpy(b->h_cams, traj, sizeof(pc_camera_state) * b->v.nf);
+    PC_CUDA(c, cudaMemcpyAsync(dst, b->h_cams, sizeof(pc_camera_state) * b->v.nf, cudaMemcpyHostToDevice, c->compute));
     return PC_OK;
 }
 
-// TotalCost (lev_marq.h:773-824): refresh the per-keypoint intersections (cache semantics of
-// refiner.cc:323-350), then per-edge normalised robust cost.
-static int ba_total_cost(pc_ctx* c, BAData* b, const pc_camera_state* traj, const Loss& loss, float* cost) {
-    int rc = upload_traj(c, b, traj);
-    if (rc) return rc;
-    cudaStream_t st = c->compute;
-    span_begin(c, KF_BA, st);
-    launch_ba_refresh_points(b->v, mesh_view(c->mesh), st);
-    launch_ba_cost(b->v, loss, st);
-    span_end(c, st);
-    rc = check_launch(c, "ba cost", 3);
-    if (rc) return rc;
-    PC_CUDA(c, cudaMemcpyAsync(cost, b->d_scalars, sizeof(float), cudaMemcpyDeviceToHost, st));
-    PC_CUDA(c, cudaStreamSynchronize(st));
-    return PC_OK;
+static BAView view_with(const BAData* b, const pc_camera_state* cams) {
+    BAView v = b->v;
+    v.cams = cams;
+    return v;
 }
 
-static int ba_build(pc_ctx* c, BAData* b, const pc_camera_state* traj, const Loss& loss, float* grad_norm) {
-    int rc = upload_traj(c, b, traj);
-    if (rc) return rc;
-    cudaStream_t st = c->compute;
-    span_begin(c, KF_BA, st);
-    launch_ba_build(b->v, mesh_view(c->mesh), loss, st);
-    launch_ba_assemble(b->v, st);
-    span_end(c, st);
-    rc = check_launch(c, "ba build", 3);
-    if (rc) return rc;
-    if (grad_norm) {
-        PC_CUDA(c, cudaMemcpyAsync(grad_norm, b->d_scalars + 1, sizeof(float), cudaMemcpyDeviceToHost, st));
-        PC_CUDA(c, cudaStreamSynchronize(st));
+// refresh + cost of `cams` -> *cost_out (device).  TotalCost (lev_marq.h:773-824): refresh the per-keypoint
+// intersections (cache semantics of refiner.cc:323-350), then the per-edge normalised robust cost.
+static int enqueue_cost(pc_ctx* c, BAData* b, const pc_camera_state* cams, const Loss& loss, const BALmState* st, int gate,
+                        float* cost_out) {
+    cudaStream_t s = c->compute;
+    const BAView v = view_with(b, cams);
+    span_begin(c, KF_BA, s);
+    launch_ba_refresh_points(v, mesh_view(c->mesh), st, gate, s);
+    if (b->sharded) {
+        // own edges only, then every rank receives every edge's cost (each produced by exactly one rank)
+        if (v.n_edges > 0) launch_ba_cost_edges(v, loss, st, gate, s);
+        int rc = comm_allgather_inplace(c, v.edge_cost, (size_t)b->edges_per_rank, s);
+        if (rc) return rc;
+        launch_ba_cost_sum(v, st, gate, cost_out, s);
+    } else {
+        launch_ba_cost(v, loss, st, gate, cost_out, s);
     }
-    return PC_OK;
+    span_end(c, s);
+    return check_launch(c, "ba cost", 3);
+}
+
+// BuildNormalEquations (lev_marq.h:653-771) of `cams` into band / jtr / diag
+static int enqueue_build(pc_ctx* c, BAData* b, const pc_camera_state* cams, const Loss& loss, const BALmState* st, int gate) {
+    cudaStream_t s = c->compute;
+    const BAView v = view_with(b, cams);
+    span_begin(c, KF_BA, s);
+    launch_ba_build(v, mesh_view(c->mesh), loss, st, gate, s);
+    if (b->sharded) {
+        int rc = comm_allgather_inplace(c, v.edge_pair, (size_t)b->edges_per_rank * v.pair_stride, s);
+        if (rc) return rc;
+    }
+    launch_ba_assemble(v, st, gate, s);
+    span_end(c, s);
+    return check_launch(c, "ba build", 3);
 }
 
 }  // namespace pc
@@ -98,7 +127,11 @@ int pc_ba_load(pc_ctx* c, const pc_ba_problem* pr) {
     if (!c->mesh || !c->mesh->d_nodes) return fail(c, PC_ERR_STATE, "no mesh set");
     PC_CHECK(c, pr->num_frames > 2, "traj.Count() > 2");                         // refiner.cc:661
     PC_CHECK(c, pr->kp_offsets && pr->num_edges >= 0 && (pr->num_edges == 0 || pr->edges), "bad arrays");
-    if (c->ba) { free_ba(c->ba); c->ba = nullptr; }
+    if (c->ba) {
+        PC_CUDA(c, cudaStreamSynchronize(c->compute));
+        free_ba(c->ba);
+        c->ba = nullptr;
+    }
     BAData* b = new BAData();
     c->ba = b;
     BAView& v = b->v;
@@ -149,10 +182,16 @@ int pc_ba_load(pc_ctx* c, const pc_ba_problem* pr) {
         edge_weight[e] = 1.0f / ((float)dist + 1.0f);
     }
     std::vector<int> inc_off(nf + 1, 0), inc_edges;
-    for (int f = 0; f < nf; f++) {
-        for (int e = 0; e < pr->num_edges; e++)
-            if (pr->edges[e].src_frame_idx == f || pr->edges[e].tgt_frame_idx == f) inc_edges.push_back(e);
-        inc_off[f + 1] = (int)inc_edges.size();
+    {
+        std::vector<std::vector<int>> inc(nf);
+        for (int e = 0; e < pr->num_edges; e++) {                 // ascending edge order per frame
+            inc[pr->edges[e].src_frame_idx].push_back(e);
+            inc[pr->edges[e].tgt_frame_idx].push_back(e);
+        }
+        for (int f = 0; f < nf; f++) {
+            inc_edges.insert(inc_edges.end(), inc[f].begin(), inc[f].end());
+            inc_off[f + 1] = (int)inc_edges.size();
+        }
     }
     int rc;
     if ((rc = dev_upload(c, b, &v.kps, pr->keypoints, (size_t)v.n_kps * 2))) return rc;
@@ -171,11 +210,18 @@ int pc_ba_load(pc_ctx* c, const pc_ba_problem* pr) {
     if ((rc = dev_alloc(c, b, &v.pt_valid, (size_t)v.n_kps))) return rc;
     PC_CUDA(c, cudaMemset(v.pt_valid, 0, std::max(v.n_kps, 1)));
     if ((rc = dev_alloc(c, b, &b->d_cams, (size_t)nf))) return rc;
+    if ((rc = dev_alloc(c, b, &b->d_cams_new, (size_t)nf))) return rc;
     v.cams = b->d_cams;
-    if ((rc = dev_alloc(c, b, &v.edge_cost, (size_t)pr->num_edges))) return rc;
+    // per-edge arrays are padded so that an all-gather of equal chunks covers them (edge-sharded refine)
+    const int world = std::max(1, comm_world(c));
+    b->edges_per_rank = (pr->num_edges + world - 1) / world;
+    b->n_edges_padded = std::max(1, b->edges_per_rank * world);
+    if ((rc = dev_alloc(c, b, &v.edge_cost, (size_t)b->n_edges_padded))) return rc;
+    PC_CUDA(c, cudaMemset(v.edge_cost, 0, sizeof(float) * b->n_edges_padded));
     const int NP = 2 * v.p;
     v.pair_stride = NP * (NP + 1) / 2 + NP + 1;
-    if ((rc = dev_alloc(c, b, &v.edge_pair, (size_t)pr->num_edges * v.pair_stride))) return rc;
+    if ((rc = dev_alloc(c, b, &v.edge_pair, (size_t)b->n_edges_padded * v.pair_stride))) return rc;
+    PC_CUDA(c, cudaMemset(v.edge_pair, 0, sizeof(float) * (size_t)b->n_edges_padded * v.pair_stride));
     const size_t band_n = (size_t)nf * kBandBlocks * v.p * v.p;
     if ((rc = dev_alloc(c, b, &v.band, band_n))) return rc;
     if ((rc = dev_alloc(c, b, &v.lband, band_n))) return rc;
@@ -184,7 +230,36 @@ int pc_ba_load(pc_ctx* c, const pc_ba_problem* pr) {
     if ((rc = dev_alloc(c, b, &v.step, (size_t)nf * v.p))) return rc;
     if ((rc = dev_alloc(c, b, &v.tmp, (size_t)nf * v.p))) return rc;
     if ((rc = dev_alloc(c, b, &b->d_scalars, (size_t)8))) return rc;
+    PC_CUDA(c, cudaMemset(b->d_scalars, 0, sizeof(float) * 8));
     v.scalars = b->d_scalars;
+    if ((rc = dev_alloc(c, b, &b->d_expected, (size_t)nf))) return rc;
+    if ((rc = dev_alloc(c, b, &b->d_state, (size_t)1))) return rc;
+    if ((rc = dev_alloc(c, b, &b->d_edge_mask, (size_t)b->n_edges_padded))) return rc;
+    v.edge_mask = nullptr;
+    PC_CUDA(c, cudaMallocHost(&b->h_state, sizeof(BALmState)));
+    PC_CUDA(c, cudaMallocHost(&b->h_cams, sizeof(pc_camera_state) * nf));
+    return PC_OK;
+}
+
+int pc_ba_set_edge_shard(pc_ctx* c, int on) {
+    PC_CUDA(c, cudaSetDevice(c->device));
+    BAData* b = c->ba;
+    if (!b) return fail(c, PC_ERR_STATE, "no refine problem loaded");
+    if (!on) {
+        b->sharded = false;
+        b->v.edge_mask = nullptr;
+        return PC_OK;
+    }
+    const int world = comm_world(c), rank = comm_rank(c);
+    if (world < 1) return fail(c, PC_ERR_STATE, "pc_comm_init has not been called on this context");
+    if (b->edges_per_rank * world != b->n_edges_padded || b->edges_per_rank * world < b->v.n_edges)
+        return fail(c, PC_ERR_STATE, "the refine problem was loaded before pc_comm_init: load it again");
+    std::vector<uint8_t> mask((size_t)b->n_edges_padded, 0);
+    for (int e = rank * b->edges_per_rank; e < std::min((rank + 1) * b->edges_per_rank, b->v.n_edges); e++) mask[e] = 1;
+    PC_CUDA(c, cudaMemcpy(b->d_edge_mask, mask.data(), mask.size(), cudaMemcpyHostToDevice));
+    b->v.edge_mask = b->d_edge_mask;
+    b->sharded = world > 1;
+    if (!b->sharded) b->v.edge_mask = nullptr;
     return PC_OK;
 }
 
@@ -200,12 +275,17 @@ int pc_ba_read_cache(pc_ctx* c, uint32_t* out, int cap) {
 
 int pc_ba_cost(pc_ctx* c, const pc_camera_state* traj, const pc_bundle_opts* bo, float* cost_out) {
     PC_CUDA(c, cudaSetDevice(c->device));
-    if (!c->ba) return fail(c, PC_ERR_STATE, "no refine problem loaded");
+    BAData* b = c->ba;
+    if (!b) return fail(c, PC_ERR_STATE, "no refine problem loaded");
     int rc = validate_bundle_opts(c, bo);
     if (rc) return rc;
     PC_CHECK(c, traj && cost_out, "bad arguments");
     const Loss loss = make_loss(bo->loss_type, bo->loss_scale);
-    return ba_total_cost(c, c->ba, traj, loss, cost_out);
+    if ((rc = upload_traj(c, b, traj, b->d_cams))) return rc;
+    if ((rc = enqueue_cost(c, b, b->d_cams, loss, nullptr, GATE_NONE, b->d_scalars))) return rc;
+    PC_CUDA(c, cudaMemcpyAsync(cost_out, b->d_scalars, sizeof(float), cudaMemcpyDeviceToHost, c->compute));
+    PC_CUDA(c, cudaStreamSynchronize(c->compute));
+    return PC_OK;
 }
 
 int pc_ba_normal_equations(pc_ctx* c, const pc_camera_state* traj, const pc_bundle_opts* bo, float* JtJ_blocks,
@@ -217,13 +297,35 @@ int pc_ba_normal_equations(pc_ctx* c, const pc_camera_state* traj, const pc_bund
     if (rc) return rc;
     PC_CHECK(c, traj != nullptr, "bad arguments");
     const Loss loss = make_loss(bo->loss_type, bo->loss_scale);
-    rc = ba_build(c, b, traj, loss, nullptr);
-    if (rc) return rc;
+    if ((rc = upload_traj(c, b, traj, b->d_cams))) return rc;
+    if ((rc = enqueue_build(c, b, b->d_cams, loss, nullptr, GATE_NONE))) return rc;
     const BAView& v = b->v;
     PC_CUDA(c, cudaStreamSynchronize(c->compute));
     if (JtJ_blocks)
         PC_CUDA(c, cudaMemcpy(JtJ_blocks, v.band, sizeof(float) * (size_t)v.nf * kBandBlocks * v.p * v.p, cudaMemcpyDeviceToHost));
     if (Jtr) PC_CUDA(c, cudaMemcpy(Jtr, v.jtr, sizeof(float) * (size_t)v.nf * v.p, cudaMemcpyDeviceToHost));
+    return PC_OK;
+}
+
+// Solves the loaded normal equations (the last pc_ba_normal_equations) with damping lambda: step = -(A_damped)^-1 Jtr
+// (ComputeStep, lev_marq.h:826-841).  Test / profiling entry point of K14; returns PC_ERR_STATE if the
+// factorisation hits a non-positive pivot.
+int pc_ba_solve_step(pc_ctx* c, float lambda, float* step_out, float* step_norm_out) {
+    PC_CUDA(c, cudaSetDevice(c->device));
+    BAData* b = c->ba;
+    if (!b) return fail(c, PC_ERR_STATE, "no refine problem loaded");
+    cudaStream_t s = c->compute;
+    span_begin(c, KF_BA, s);
+    launch_ba_solve(b->v, nullptr, lambda, s);
+    span_end(c, s);
+    int rc = check_launch(c, "ba solve", 1);
+    if (rc) return rc;
+    float sc[5];
+    PC_CUDA(c, cudaMemcpyAsync(sc, b->d_scalars, sizeof(sc), cudaMemcpyDeviceToHost, s));
+    PC_CUDA(c, cudaStreamSynchronize(s));
+    if (sc[4] == 0.f) return fail(c, PC_ERR_STATE, "the damped normal equations are not positive definite");
+    if (step_norm_out) *step_norm_out = sc[2];
+    if (step_out) PC_CUDA(c, cudaMemcpy(step_out, b->v.step, sizeof(float) * (size_t)b->v.nf * b->v.p, cudaMemcpyDeviceToHost));
     return PC_OK;
 }
 
@@ -236,90 +338,84 @@ int pc_ba_solve(pc_ctx* c, const pc_bundle_opts* bo, pc_camera_state* traj, pc_b
     if (rc) return rc;
     PC_CHECK(c, traj != nullptr, "bad arguments");
     const BAView& v = b->v;
-    const int nf = v.nf, p = v.p;
+    const int nf = v.nf;
     for (int f = 0; f < nf; f++)
         if (traj[f].filled == 0.f) return fail(c, PC_ERR_INVALID, "check failed: traj.IsFrameFilled(frame)");   // refiner.cc:662-665
     const Loss loss = make_loss(bo->loss_type, bo->loss_scale);
     const Bounds bounds = get_bounds(traj[0]);                                      // refiner.cc:687
-    cudaStream_t st = c->compute;
-    std::vector<pc_camera_state> params(traj, traj + nf), params_new(nf);
-    std::vector<float> step((size_t)nf * p);
+    cudaStream_t s = c->compute;
 
-    // LevMarqSparseSolver::Solve (lev_marq.h:492-588)
-    pc_bundle_stats stats{};
-    rc = ba_total_cost(c, b, params.data(), loss, &stats.cost);
-    if (rc) return rc;
-    stats.initial_cost = stats.cost;
-    stats.grad_norm = -1.f;
-    stats.step_norm = -1.f;
-    stats.invalid_steps = 0;
-    stats.lambda = bo->initial_lambda;
-    float vfac = 2.0f;
-    bool rebuild = true;
-    for (stats.iterations = 0; stats.iterations < bo->max_iterations; ++stats.iterations) {
-        if (rebuild) {
-            rc = ba_build(c, b, params.data(), loss, &stats.grad_norm);
-            if (rc) return rc;
-            if (stats.grad_norm < bo->gradient_tol) break;
+    // LevMarqSparseSolver::Solve (lev_marq.h:492-588): stats.cost = TotalCost(params); then the device loop
+    if ((rc = upload_traj(c, b, traj, b->d_cams))) return rc;
+    if ((rc = enqueue_cost(c, b, b->d_cams, loss, nullptr, GATE_NONE, b->d_scalars))) return rc;
+    float cost0 = 0.f;
+    PC_CUDA(c, cudaMemcpyAsync(&cost0, b->d_scalars, sizeof(float), cudaMemcpyDeviceToHost, s));
+    PC_CUDA(c, cudaStreamSynchronize(s));
+    BALmState& hs = *b->h_state;
+    memset(&hs, 0, sizeof(hs));
+    hs.gradient_tol = bo->gradient_tol;
+    hs.step_tol = bo->step_tol;
+    hs.min_lambda = bo->min_lambda;
+    hs.max_lambda = bo->max_lambda;
+    hs.max_iterations = bo->max_iterations;
+    hs.cost = cost0;
+    hs.initial_cost = cost0;
+    hs.lambda = bo->initial_lambda;
+    hs.v = 2.0f;
+    hs.rebuild = 1;
+    hs.grad_norm = -1.f;
+    hs.step_norm = -1.f;
+    hs.done = bo->max_iterations == 0 ? 1 : 0;
+    PC_CUDA(c, cudaMemcpyAsync(b->d_state, &hs, sizeof(hs), cudaMemcpyHostToDevice, s));
+    PC_CUDA(c, cudaStreamSynchronize(s));          // hs is reused as the read-back buffer below
+
+    // Without a callback the loop state is looked at every kChunk iterations (iterations enqueued after the
+    // loop has ended are launches that return at once); with one, after every iteration.
+    const uint64_t kChunk = cb != nullptr ? 1 : 4;
+    bool stopped_by_callback = false;
+    pc_bundle_stats last_snap{};
+    bool done = hs.done != 0;
+    for (uint64_t it = 0; !done && it < bo->max_iterations + 1; it += kChunk) {
+        for (uint64_t k = 0; k < kChunk; k++) {
+            if ((rc = enqueue_build(c, b, b->d_cams, loss, b->d_state, GATE_BUILD))) return rc;
+            span_begin(c, KF_BA, s);
+            launch_ba_solve(v, b->d_state, 0.f, s);                                  // ComputeStep
+            launch_ba_step(v, b->d_state, b->d_cams, b->d_cams_new, bounds, b->d_expected, s);
+            span_end(c, s);
+            if ((rc = check_launch(c, "ba solve", 2))) return rc;
+            if ((rc = enqueue_cost(c, b, b->d_cams_new, loss, b->d_state, GATE_EVAL, b->d_scalars + 5))) return rc;
+            span_begin(c, KF_BA, s);
+            launch_ba_decide(v, b->d_state, b->d_cams, b->d_cams_new, b->d_expected, b->d_scalars + 5, s);
+            span_end(c, s);
+            if ((rc = check_launch(c, "ba decide", 1))) return rc;
         }
-        span_begin(c, KF_BA, st);
-        launch_ba_solve(v, stats.lambda, st);                                       // ComputeStep
-        span_end(c, st);
-        rc = check_launch(c, "ba solve", 1);
-        if (rc) return rc;
-        float sc[5];
-        PC_CUDA(c, cudaMemcpyAsync(sc, b->d_scalars, sizeof(sc), cudaMemcpyDeviceToHost, st));
-        PC_CUDA(c, cudaStreamSynchronize(st));
-        if (sc[4] == 0.f) {                                                          // factorisation failed
-            stats.invalid_steps++;
-            if (stats.lambda == bo->max_lambda) break;
-            stats.lambda = std::min(bo->max_lambda, stats.lambda * vfac);
-            vfac = 2 * vfac;
-            rebuild = false;
-            continue;
-        }
-        stats.step_norm = sc[2];
-        if (stats.step_norm < bo->step_tol) break;
-        PC_CUDA(c, cudaMemcpyAsync(step.data(), v.step, sizeof(float) * step.size(), cudaMemcpyDeviceToHost, st));
-        PC_CUDA(c, cudaStreamSynchronize(st));
-        // GlobalRefinementProblem::Step (refiner.cc:618-646): first and last cameras are constant
-        params_new[0] = params[0];
-        params_new[nf - 1] = params[nf - 1];
-        for (int f = 1; f < nf - 1; f++)
-            camera_step(params[f], &step[(size_t)f * p], b->opt_f, b->opt_pp, bounds, params_new[f]);
-        float cost_new = 0.f;
-        rc = ba_total_cost(c, b, params_new.data(), loss, &cost_new);
-        if (rc) return rc;
-        if (cost_new < stats.cost) {
-            const float actual = cost_new - stats.cost;
-            span_begin(c, KF_BA, st);
-            launch_ba_expected_change(v, st);
-            span_end(c, st);
-            rc = check_launch(c, "ba expected change", 1);
-            if (rc) return rc;
-            float expected = 0.f;
-            PC_CUDA(c, cudaMemcpyAsync(&expected, b->d_scalars + 3, sizeof(float), cudaMemcpyDeviceToHost, st));
-            PC_CUDA(c, cudaStreamSynchronize(st));
-            const float rho = actual / expected;
-            if (rho > 0) {
-                const float factor = (float)std::max(1.0 / 3.0, 1.0 - pow(2.0 * rho - 1.0, 3));   // Float factor
-                stats.lambda = std::min(std::max(stats.lambda * factor, bo->min_lambda), bo->max_lambda);
+        PC_CUDA(c, cudaMemcpyAsync(&hs, b->d_state, sizeof(hs), cudaMemcpyDeviceToHost, s));
+        PC_CUDA(c, cudaStreamSynchronize(s));
+        done = hs.done != 0;
+        if (cb != nullptr && hs.snap_valid) {                                         // lev_marq.h:576-580
+            last_snap = hs.snap;
+            if (!cb(&hs.snap, user)) {
+                stopped_by_callback = true;
+                break;
             }
-            std::swap(params, params_new);
-            stats.cost = cost_new;
-            vfac = 2;
-            rebuild = true;
-        } else {
-            stats.invalid_steps++;
-            if (stats.lambda == bo->max_lambda) break;
-            stats.lambda = std::min(bo->max_lambda, stats.lambda * vfac);
-            vfac = 2 * vfac;
-            rebuild = false;
         }
-        if (cb != nullptr && !cb(&stats, user)) break;
+    }
+    pc_bundle_stats stats{};
+    if (stopped_by_callback) {
+        stats = last_snap;                          // the `break` comes before ++iterations
+    } else {
+        stats.iterations = hs.iterations;
+        stats.initial_cost = hs.initial_cost;
+        stats.cost = hs.cost;
+        stats.lambda = hs.lambda;
+        stats.invalid_steps = hs.invalid_steps;
+        stats.step_norm = hs.step_norm;
+        stats.grad_norm = hs.grad_norm;
     }
     if (cb != nullptr) cb(&stats, user);
-    memcpy(traj, params.data(), sizeof(pc_camera_state) * nf);
+    PC_CUDA(c, cudaMemcpyAsync(b->h_cams, b->d_cams, sizeof(pc_camera_state) * nf, cudaMemcpyDeviceToHost, s));
+    PC_CUDA(c, cudaStreamSynchronize(s));
+    memcpy(traj, b->h_cams, sizeof(pc_camera_state) * nf);
     if (stats_out) *stats_out = stats;
     return PC_OK;
 }

@@ -309,6 +309,7 @@ pc_ctx::~pc_ctx() {
     if (track) free_track_chain(track);
     if (mesh) free_mesh(mesh);
     if (ba) free_ba(ba);
+    if (comm) free_comm(comm);
     if (side) cudaStreamDestroy(side);
     if (compute) cudaStreamDestroy(compute);
     if (h2d) cudaStreamDestroy(h2d);

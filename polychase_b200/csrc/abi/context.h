@@ -98,6 +98,7 @@ struct TrackChain {
 
 struct MeshData;   // track.cu
 struct BAData;     // ba.cu
+struct CommData;   // comm.cu
 
 }  // namespace pc
 
@@ -157,6 +158,7 @@ struct pc_ctx {
     pc::MeshData* mesh = nullptr;
     pc::BAData* ba = nullptr;
     pc::TrackChain* track = nullptr;
+    pc::CommData* comm = nullptr;
 
     ~pc_ctx();
 };
@@ -193,5 +195,6 @@ void free_track_chain(TrackChain*);
 int track_chain_enqueue(pc_ctx* c, Stage& st, int32_t frame_id, bool is_halo, int cap);
 int track_chain_collect(pc_ctx* c, Stage& st, pc_frame_result* out);
 void free_ba(BAData*);
+void free_comm(CommData*);
 
 }  // namespace pc

@@ -67,7 +67,14 @@ __device__ __forceinline__ bool intersect_tri(V3 o, V3 d, V3 p1, V3 p2, V3 p3, V
 }  // namespace
 
 // ---- first half of Evaluate, once per referenced keypoint (refiner.cc:306-350) -----------
-__global__ void __launch_bounds__(128) ba_refresh_kernel(BAView v, MeshView mesh) {
+__device__ __forceinline__ bool gate_closed(const BALmState* st, int gate) {
+    if (st == nullptr || gate == GATE_NONE) return false;
+    if (st->done) return true;
+    return gate == GATE_BUILD ? !st->rebuild : st->skip != 0;
+}
+
+__global__ void __launch_bounds__(128) ba_refresh_kernel(BAView v, MeshView mesh, const BALmState* st, int gate) {
+    if (gate_closed(st, gate)) return;
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= v.n_kps) return;
     if (!v.referenced[g]) { v.pt_valid[g] = 0; return; }
@@ -107,18 +114,23 @@ __global__ void __launch_bounds__(128) ba_refresh_kernel(BAView v, MeshView mesh
     }
 }
 
-void launch_ba_refresh_points(const BAView& v, const MeshView& mesh, cudaStream_t s) {
+void launch_ba_refresh_points(const BAView& v, const MeshView& mesh, const BALmState* st, int gate, cudaStream_t s) {
     if (v.n_kps <= 0) return;      // every keypoint fell outside the projected mesh bbox: nothing to evaluate
-    ba_refresh_kernel<<<(v.n_kps + 127) / 128, 128, 0, s>>>(v, mesh);
+    ba_refresh_kernel<<<(v.n_kps + 127) / 128, 128, 0, s>>>(v, mesh, st, gate);
 }
 
 // ---- TotalCost: one CTA per edge (lev_marq.h:773-824, refiner.cc:354-360) -----------------
 constexpr int BA_THREADS = 256;
 
-__global__ void __launch_bounds__(BA_THREADS) ba_cost_kernel(BAView v, Loss loss) {
+__global__ void __launch_bounds__(BA_THREADS) ba_cost_kernel(BAView v, Loss loss, const BALmState* st, int gate) {
     __shared__ double red_sum[BA_THREADS / 32];
     __shared__ int red_cnt[BA_THREADS / 32];
+    if (gate_closed(st, gate)) return;
     const int e = blockIdx.x;
+    if (v.edge_mask != nullptr && !v.edge_mask[e]) {           // another rank's edge
+        if (threadIdx.x == 0) v.edge_cost[e] = 0.f;
+        return;
+    }
     const pc_ba_edge ed = v.edges[e];
     const Cam ct = make_cam(v.cams[ed.tgt_frame_idx]);
     const int koff = v.kp_offsets[ed.src_frame_idx];
@@ -151,15 +163,31 @@ __global__ void __launch_bounds__(BA_THREADS) ba_cost_kernel(BAView v, Loss loss
     }
 }
 
-__global__ void ba_sum_cost_kernel(BAView v) {
+// cost = sum of the per-edge costs in edge order (float32, like the reference's cost += in TotalCost with one
+// thread, lev_marq.h:818): a warp walks the list 32 at a time, lane 0 adds each group's terms in order.
+__global__ void __launch_bounds__(32) ba_sum_cost_kernel(BAView v, const BALmState* st, int gate, float* cost_out) {
+    if (gate_closed(st, gate)) return;
     float c = 0.f;
-    for (int e = 0; e < v.n_edges; e++) c += v.edge_cost[e];
-    v.scalars[0] = c;
+    for (int e0 = 0; e0 < v.n_edges; e0 += 32) {
+        const int e = e0 + threadIdx.x;
+        const float x = e < v.n_edges ? v.edge_cost[e] : 0.f;
+#pragma unroll
+        for (int l = 0; l < 32; l++) c += __shfl_sync(0xffffffffu, x, l);
+    }
+    if (threadIdx.x == 0) *cost_out = c;
 }
 
-void launch_ba_cost(const BAView& v, const Loss& loss, cudaStream_t s) {
-    if (v.n_edges > 0) ba_cost_kernel<<<v.n_edges, BA_THREADS, 0, s>>>(v, loss);
-    ba_sum_cost_kernel<<<1, 1, 0, s>>>(v);
+void launch_ba_cost_edges(const BAView& v, const Loss& loss, const BALmState* st, int gate, cudaStream_t s) {
+    if (v.n_edges > 0) ba_cost_kernel<<<v.n_edges, BA_THREADS, 0, s>>>(v, loss, st, gate);
+}
+
+void launch_ba_cost_sum(const BAView& v, const BALmState* st, int gate, float* cost_out, cudaStream_t s) {
+    ba_sum_cost_kernel<<<1, 32, 0, s>>>(v, st, gate, cost_out);
+}
+
+void launch_ba_cost(const BAView& v, const Loss& loss, const BALmState* st, int gate, float* cost_out, cudaStream_t s) {
+    launch_ba_cost_edges(v, loss, st, gate, s);
+    launch_ba_cost_sum(v, st, gate, cost_out, s);
 }
 
 // ---- BuildNormalEquations: one CTA per edge ---------------------------------------------------
@@ -288,7 +316,7 @@ __device__ __forceinline__ void ba_edge_accumulate(const BAView& v, const MeshVi
 // P == 6: one half (256 threads).  P == 9: two halves of 128 threads that each evaluate every
 // residual and keep rows [0,12) resp. [12,18) of the 18x18 lower triangle (register budget).
 template <int P>
-__global__ void __launch_bounds__(256) ba_build_kernel(BAView v, MeshView mesh, Loss loss) {
+__global__ void __launch_bounds__(256) ba_build_kernel(BAView v, MeshView mesh, Loss loss, const BALmState* st, int gate) {
     constexpr int NP = 2 * P;
     constexpr int HALVES = P == 6 ? 1 : 2;
     constexpr int HT = 256 / HALVES;          // threads per half
@@ -296,9 +324,10 @@ __global__ void __launch_bounds__(256) ba_build_kernel(BAView v, MeshView mesh, 
     constexpr int SPLIT = 12;
     __shared__ float s_acc[8 * 128];
     __shared__ int s_cnt[8];
+    if (gate_closed(st, gate)) return;
     const int e = blockIdx.x;
     const pc_ba_edge ed = v.edges[e];
-    const float ew = v.edge_weight[e];
+    const float ew = (v.edge_mask != nullptr && !v.edge_mask[e]) ? 0.f : v.edge_weight[e];   // another rank's edge: no contribution
     float* out = v.edge_pair + (size_t)e * v.pair_stride;
     const int half = threadIdx.x / HT;
     if (ew == 0.f) {                                            // lev_marq.h:670-673
@@ -337,10 +366,10 @@ __global__ void __launch_bounds__(256) ba_build_kernel(BAView v, MeshView mesh, 
     if (threadIdx.x == 0) out[TRI + NP] = (float)n;
 }
 
-void launch_ba_build(const BAView& v, const MeshView& mesh, const Loss& loss, cudaStream_t s) {
+void launch_ba_build(const BAView& v, const MeshView& mesh, const Loss& loss, const BALmState* st, int gate, cudaStream_t s) {
     if (v.n_edges <= 0) return;
-    if (v.p == 6) ba_build_kernel<6><<<v.n_edges, 256, 0, s>>>(v, mesh, loss);
-    else ba_build_kernel<9><<<v.n_edges, 256, 0, s>>>(v, mesh, loss);
+    if (v.p == 6) ba_build_kernel<6><<<v.n_edges, 256, 0, s>>>(v, mesh, loss, st, gate);
+    else ba_build_kernel<9><<<v.n_edges, 256, 0, s>>>(v, mesh, loss, st, gate);
 }
 
 // ---- assembly into the block-banded matrix: one CTA per frame -----------------------------------
@@ -352,7 +381,8 @@ __device__ __forceinline__ float pair_at(const float* pr, int a, int b) {   // s
     return pr[a * (a + 1) / 2 + b];
 }
 
-__global__ void __launch_bounds__(256) ba_assemble_kernel(BAView v) {
+__global__ void __launch_bounds__(256) ba_assemble_kernel(BAView v, const BALmState* st, int gate) {
+    if (gate_closed(st, gate)) return;
     const int i = blockIdx.x;
     const int p = v.p, pp = p * p, NP = 2 * p, TRI = NP * (NP + 1) / 2;
     float* band_i = v.band + (size_t)i * kBandBlocks * pp;
@@ -410,217 +440,9 @@ __global__ void __launch_bounds__(1024) ba_grad_norm_kernel(BAView v) {
     }
 }
 
-void launch_ba_assemble(const BAView& v, cudaStream_t s) {
-    ba_assemble_kernel<<<v.nf, 256, 0, s>>>(v);
-    ba_grad_norm_kernel<<<1, 1024, 0, s>>>(v);
-}
-
-// ---- K14: blocked banded Cholesky + solve on one CTA ---------------------------------------------
-// lband[i][k] (k = 0..8) holds block (i, i-k) of the damped matrix, then of its factor L.
-__global__ void __launch_bounds__(1024) ba_solve_kernel(BAView v, float lambda) {
-    extern __shared__ float sm[];
-    const int p = v.p, pp = p * p, nf = v.nf;
-    const int tid = threadIdx.x, nt = blockDim.x;
-    float* L = v.lband;
-    __shared__ int s_ok;
-    // copy + damp: diag <- JtJ_diag * (1 + lambda)  (lev_marq.h:828)
-    const float damp = (float)(1.0 + (double)lambda);
-    for (int idx = tid; idx < nf * kBandBlocks * pp; idx += nt) {
-        const int i = idx / (kBandBlocks * pp), rem = idx - i * kBandBlocks * pp;
-        const int k = rem / pp, a = (rem - k * pp) / p, b = rem - k * pp - a * p;
-        float val = v.band[idx];
-        if (k == 0 && a == b) val = v.diag[i * p + a] * damp;
-        L[idx] = val;
-    }
-    if (tid == 0) s_ok = 1;
-    __syncthreads();
-    // Working set of one elimination step in shared memory: the diagonal block and the panel rows.
-    // Every global access of a phase is then one batch of independent loads (one L2 round trip per
-    // phase) instead of a chain of dependent ones inside a single thread.
-    __shared__ float Ds[9 * 9];                               // diagonal block (p <= 9)
-    __shared__ float Xs[(kBandBlocks - 1) * 9][9];            // panel rows X = B L_kk^-T
-    for (int kf = 0; kf < nf; kf++) {
-        float* D = L + ((size_t)kf * kBandBlocks) * pp;          // diagonal block of column kf
-        if (tid < pp) Ds[tid] = D[tid];
-        const int ilast = min(kf + kBandBlocks - 1, nf - 1);
-        const int nrows = (ilast - kf) * p;
-        float brow[9];
-        if (tid < nrows) {                                        // this thread's panel row, fetched meanwhile
-            const int i = kf + 1 + tid / p, a = tid % p;
-            const float* B = L + ((size_t)i * kBandBlocks + (i - kf)) * pp + a * p;
-            for (int c = 0; c < p; c++) brow[c] = B[c];
-        }
-        __syncthreads();
-        if (tid == 0) {                                           // unblocked LLT of the p x p block
-            for (int c = 0; c < p && s_ok; c++) {
-                float x = Ds[c * p + c];
-                for (int j = 0; j < c; j++) x -= Ds[c * p + j] * Ds[c * p + j];
-                if (!(x > 0.f)) { s_ok = 0; break; }
-                x = sqrtf(x);
-                Ds[c * p + c] = x;
-                for (int r = c + 1; r < p; r++) {
-                    float s = Ds[r * p + c];
-                    for (int j = 0; j < c; j++) s -= Ds[r * p + j] * Ds[c * p + j];
-                    Ds[r * p + c] = s / x;
-                }
-            }
-            for (int r = 0; r < p; r++)
-                for (int c = r + 1; c < p; c++) Ds[r * p + c] = 0.f;
-        }
-        __syncthreads();
-        if (!s_ok) break;
-        if (tid < pp) D[tid] = Ds[tid];
-        // panel: X = B * L_kk^-T for every block (i, kf), i in (kf, ilast]; one thread per row
-        if (tid < nrows) {
-            const int i = kf + 1 + tid / p, a = tid % p;
-            float* B = L + ((size_t)i * kBandBlocks + (i - kf)) * pp + a * p;
-            for (int c = 0; c < p; c++) {
-                float s = brow[c];
-                for (int j = 0; j < c; j++) s -= brow[j] * Ds[c * p + j];
-                brow[c] = s / Ds[c * p + c];
-            }
-            for (int c = 0; c < p; c++) { B[c] = brow[c]; Xs[tid][c] = brow[c]; }
-        }
-        __syncthreads();
-        // trailing update: block (i, j) -= X_i X_j^T for kf < j <= i <= ilast
-        const int nb = ilast - kf;
-        const int npairs = nb * (nb + 1) / 2;
-        for (int idx = tid; idx < npairs * pp; idx += nt) {
-            const int pr = idx / pp, a = (idx - pr * pp) / p, b = idx - pr * pp - a * p;
-            int ii = 0, acc = 0;
-            while (acc + ii + 1 <= pr) { acc += ii + 1; ii++; }   // pr -> (ii, jj), jj <= ii
-            const int jj = pr - acc;
-            const int i = kf + 1 + ii, j = kf + 1 + jj;
-            const float* Xi = Xs[ii * p + a];
-            const float* Xj = Xs[jj * p + b];
-            float s = 0.f;
-            for (int q = 0; q < p; q++) s += Xi[q] * Xj[q];
-            L[((size_t)i * kBandBlocks + (i - j)) * pp + a * p + b] -= s;
-        }
-        __syncthreads();
-    }
-    if (tid == 0) v.scalars[4] = s_ok ? 1.f : 0.f;
-    if (!s_ok) return;
-    // forward: y_i = L_ii^-1 (b_i - sum_{k=1..8} L_(i,i-k) y_(i-k)); backward: x_i = L_ii^-T (y_i - sum_k
-    // L_(i+k,i)^T x_(i+k)).  The eight off-diagonal blocks and the diagonal block of a step are staged in
-    // shared memory by all threads at once; y and x of the last eight block rows live there too.
-    __shared__ float Bs[kBandBlocks][9 * 9];                  // [0] diagonal, [k] block k of the step
-    __shared__ float win[kBandBlocks][9];                     // solution of block rows i-1.. / i+1.. (ring by i % 9)
-    float* y = v.tmp;
-    for (int i = 0; i < nf; i++) {
-        for (int idx = tid; idx < kBandBlocks * pp; idx += nt) {
-            const int k = idx / pp, e = idx - k * pp;
-            if (i - k >= 0) Bs[k][e] = L[((size_t)i * kBandBlocks + k) * pp + e];
-        }
-        __syncthreads();
-        if (tid < p) {
-            float s = v.jtr[i * p + tid];
-            for (int k = 1; k < kBandBlocks && i - k >= 0; k++) {
-                const float* yk = win[(i - k) % kBandBlocks];
-                for (int q = 0; q < p; q++) s -= Bs[k][tid * p + q] * yk[q];
-            }
-            sm[tid] = s;
-        }
-        __syncthreads();
-        if (tid == 0) {
-            float* yi = win[i % kBandBlocks];
-            for (int r = 0; r < p; r++) {
-                float s = sm[r];
-                for (int j = 0; j < r; j++) s -= Bs[0][r * p + j] * yi[j];
-                yi[r] = s / Bs[0][r * p + r];
-                y[i * p + r] = yi[r];
-            }
-        }
-        __syncthreads();
-    }
-    float* x = v.step;
-    for (int i = nf - 1; i >= 0; i--) {
-        for (int idx = tid; idx < kBandBlocks * pp; idx += nt) {
-            const int k = idx / pp, e = idx - k * pp;
-            if (k == 0) Bs[0][e] = L[((size_t)i * kBandBlocks) * pp + e];
-            else if (i + k < nf) Bs[k][e] = L[((size_t)(i + k) * kBandBlocks + k) * pp + e];   // block (i+k, i)
-        }
-        __syncthreads();
-        if (tid < p) {
-            float s = y[i * p + tid];
-            for (int k = 1; k < kBandBlocks && i + k < nf; k++) {
-                const float* xk = win[(i + k) % kBandBlocks];
-                for (int q = 0; q < p; q++) s -= Bs[k][q * p + tid] * xk[q];
-            }
-            sm[tid] = s;
-        }
-        __syncthreads();
-        if (tid == 0) {
-            float* xi = win[i % kBandBlocks];
-            for (int r = p - 1; r >= 0; r--) {
-                float s = sm[r];
-                for (int j = r + 1; j < p; j++) s -= Bs[0][j * p + r] * xi[j];
-                xi[r] = s / Bs[0][r * p + r];
-                x[i * p + r] = xi[r];
-            }
-        }
-        __syncthreads();
-    }
-    // step = -x ; step norm
-    __shared__ double red[32];
-    double a = 0.0;
-    for (int k = tid; k < nf * p; k += nt) {
-        const float sv = -x[k];
-        x[k] = sv;
-        a += (double)sv * (double)sv;
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-    if ((tid & 31) == 0) red[tid >> 5] = a;
-    __syncthreads();
-    if (tid == 0) {
-        double s = 0.0;
-        for (int k = 0; k < nt / 32; k++) s += red[k];
-        v.scalars[2] = (float)sqrt(s);
-    }
-}
-
-void launch_ba_solve(const BAView& v, float lambda, cudaStream_t s) {
-    ba_solve_kernel<<<1, 1024, 64 * sizeof(float), s>>>(v, lambda);
-}
-
-// expected_cost_change = step^T (2 Jtr + JtJ step), JtJ undamped with the clamped diagonal
-// (lev_marq.h:541-545).
-__global__ void __launch_bounds__(1024) ba_expected_change_kernel(BAView v) {
-    __shared__ double red[32];
-    const int p = v.p, pp = p * p, nf = v.nf;
-    double acc = 0.0;
-    for (int idx = threadIdx.x; idx < nf * p; idx += blockDim.x) {
-        const int i = idx / p, a = idx - i * p;
-        float s = 0.f;
-        for (int k = 0; k < kBandBlocks && i - k >= 0; k++) {          // blocks (i, i-k)
-            const float* B = v.band + ((size_t)i * kBandBlocks + k) * pp + a * p;
-            const float* sv = v.step + (i - k) * p;
-            for (int q = 0; q < p; q++) {
-                const float m = (k == 0 && q == a) ? v.diag[i * p + a] : B[q];
-                s += m * sv[q];
-            }
-        }
-        for (int k = 1; k < kBandBlocks && i + k < nf; k++) {           // blocks (i+k, i)^T
-            const float* B = v.band + ((size_t)(i + k) * kBandBlocks + k) * pp;
-            const float* sv = v.step + (i + k) * p;
-            for (int q = 0; q < p; q++) s += B[q * p + a] * sv[q];
-        }
-        acc += (double)v.step[idx] * (double)(2.f * v.jtr[idx] + s);
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        double s = 0.0;
-        for (int k = 0; k < 32; k++) s += red[k];
-        v.scalars[3] = (float)s;
-    }
-}
-
-void launch_ba_expected_change(const BAView& v, cudaStream_t s) {
-    ba_expected_change_kernel<<<1, 1024, 0, s>>>(v);
+void launch_ba_assemble(const BAView& v, const BALmState* st, int gate, cudaStream_t s) {
+    ba_assemble_kernel<<<v.nf, 256, 0, s>>>(v, st, gate);
+    if (st == nullptr) ba_grad_norm_kernel<<<1, 1024, 0, s>>>(v);   // the LM loop forms |Jtr| in its solve kernel
 }
 
 }  // namespace pc

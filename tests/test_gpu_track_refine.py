@@ -11,7 +11,10 @@ float32 summation order scatters around.  The reference's own sums are order dep
 thread-local partials in scheduling order, lev_marq.h:231-297,653-771); where a converged LM result
 amplifies that, the oracle is re-run with permuted float32 summation orders and the GPU has to sit
 inside max(1e-4, BAND x the largest deviation those few samples show) -- BAND = 2 because the maximum
-of two or three samples underestimates the spread of the distribution they are drawn from."""
+of two or three samples underestimates the spread of the distribution they are drawn from.  For the chained
+sweep the samples also include runs whose LK target positions are moved by one float32 ulp: the size of the
+per-residual arithmetic differences between any two correct float32 implementations (fused multiply-add or not,
+R X versus q X q* -- the reference's own Evaluate and EvaluateWithJacobian differ in that, pnp_problem.h:54,76)."""
 import numpy as np
 import pytest
 
@@ -166,7 +169,7 @@ def test_solve_pnp_errors(ctx_small):
         ctx_small.solve_pnp(np.zeros((5, 3), F), np.zeros((5, 2), F), cam, capi.default_bundle(loss_type=7))
 
 
-def _track_oracle_with_band(scene, opts, opt_f=False, seeds=(1, 2, 3)):
+def _track_oracle_with_band(scene, opts, opt_f=False, seeds=(1, 2, 3, 4)):
     clip, kps, flows, NF = scene["clip"], scene["kps"], scene["flows"], scene["NF"]
     model = np.eye(4, dtype=F)
     start = cam_of(scene, 0)
@@ -175,8 +178,15 @@ def _track_oracle_with_band(scene, opts, opt_f=False, seeds=(1, 2, 3)):
         want = otrack.track_sequence(*args)
     band = {f: [0.0, 0.0, 0.0] for f in want}
     for s in seeds:
-        with opnp.summation(F, perm_seed=s):
-            alt = otrack.track_sequence(*args)
+        if s % 2:                                                  # odd seeds: summation order
+            with opnp.summation(F, perm_seed=s):
+                alt = otrack.track_sequence(*args)
+        else:                                                      # even seeds: one-ulp jitter of the LK targets
+            rng = np.random.default_rng(s)
+            jf = {k: (idx, np.nextafter(tgt, np.where(rng.random(tgt.shape) < 0.5, -np.inf, np.inf).astype(F)), err)
+                  for k, (idx, tgt, err) in flows.items()}
+            with opnp.summation(np.float64):
+                alt = otrack.track_sequence(kps, jf, *args[2:])
         for f in want:
             dq, dt = H.pose_close(want[f][0], alt[f][0])
             df = abs(float(alt[f][0].intrinsics.fy) - float(want[f][0].intrinsics.fy)) / abs(float(want[f][0].intrinsics.fy))
@@ -345,6 +355,17 @@ def check_cost_and_normal_equations(ctx, scene, opt_f, opt_pp, loss, seed=3):
             assert np.abs(jtr[i * p:(i + 1) * p] - g[i * p:(i + 1) * p]).max() <= RTOL * max(s, 1e-3 * np.abs(g).max())
     # first / last frame are ground truth: their blocks are empty (refiner.cc:611-612)
     assert np.all(Ag[:p, :] == 0) and np.all(Ag[-p:, :] == 0)
+    # K14 on its own (ComputeStep, lev_marq.h:826-841): the block-banded Cholesky solve of these equations against
+    # a dense float64 solve of the same float32 matrix, at two dampings
+    full = (Ag + np.tril(Ag, -1).T).astype(np.float64)
+    dg = np.clip(np.diag(Ag), 1e-6, 1e32).astype(np.float64)
+    for lam in (1e-5, 10.0):
+        Ad = full.copy()
+        np.fill_diagonal(Ad, dg * (1.0 + lam))
+        want_step = -np.linalg.solve(Ad, jtr.astype(np.float64))
+        got_step, got_norm = ctx.ba_solve_step(lam)
+        assert np.abs(got_step - want_step).max() <= 2e-3 * np.abs(want_step).max(), lam
+        assert abs(got_norm - np.linalg.norm(want_step)) <= 2e-3 * np.linalg.norm(want_step)
     return prob
 
 
