@@ -828,6 +828,8 @@ def plugin_block(ctx, args, w, h, max_corners, dev_frames, frame_bytes, n_frames
         errors = []
         t0 = time.perf_counter()
         th = core.OpticalFlowThread(core.VideoInfo(w, h, 1, F), dbp, go)
+        t_first = t_last_req = None
+        provide_s = 0.0
         while True:
             m = th.try_pop()
             if m is None:
@@ -836,7 +838,12 @@ def plugin_block(ctx, args, w, h, max_corners, dev_frames, frame_bytes, n_frames
             if isinstance(m, bool):
                 break
             if isinstance(m, core.OpticalFlowRequest):
+                t1 = time.perf_counter()
+                if t_first is None:
+                    t_first = t1 - t0
                 th.provide_frame(m.frame_id, host[image_of(m.frame_id - 1, ring)])
+                t_last_req = time.perf_counter()
+                provide_s += t_last_req - t1
             elif isinstance(m, core.CppException):
                 errors.append(m.what())
         th.join()
@@ -844,7 +851,10 @@ def plugin_block(ctx, args, w, h, max_corners, dev_frames, frame_bytes, n_frames
         pairs = 8 * F - 30
         return {"entry_point": "polychase_core.OpticalFlowThread (request / provide_frame hand-off) + SQLite database",
                 "frames": F, "directed_pairs": pairs, "wall_s": dt, "value": pairs / dt, "unit": "frame-pairs/s",
-                "frames_per_s": F / dt, "db_bytes": os.path.getsize(dbp), "errors": errors}
+                "frames_per_s": F / dt, "db_bytes": os.path.getsize(dbp), "errors": errors,
+                "breakdown_s": {"until_first_request": t_first, "inside_provide_frame": provide_s,
+                                "first_to_last_request": (t_last_req - t0 - t_first) if t_first is not None else None,
+                                "after_last_request": dt - (t_last_req - t0) if t_last_req else None}}
     finally:
         shutil.rmtree(tmp, ignore_errors=True)
 
