@@ -288,12 +288,16 @@ def main():
     ap.add_argument("--no-ba", action="store_true", help="skip the configs[4] refine block")
     ap.add_argument("--no-plugin", action="store_true", help="skip the polychase_core.OpticalFlowThread block")
     ap.add_argument("--ba-frames", type=int, default=200)
-    ap.add_argument("--plugin-frames", type=int, default=128)
+    ap.add_argument("--plugin-frames", type=int, default=256)
+    ap.add_argument("--plugin-only", action="store_true", help="run only the OpticalFlowThread block (used by the main run)")
     ap.add_argument("--depth", type=int, default=16, help="frames in flight in the streaming analyzer")
     ap.add_argument("--diag", action="store_true",
                     help="also time upload-only and download-only legs and the raw H2D copy rate (stderr)")
     args = ap.parse_args()
 
+    if args.plugin_only:
+        plugin_only(args)
+        return
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -653,7 +657,7 @@ def main():
             line["ba"] = {"error": repr(e)}
     if world == 1 and not args.no_plugin:
         try:
-            line["plugin_e2e"] = plugin_block(ctx, args, w, h, max_corners, dev_frames, frame_bytes, n_frames, image_of)
+            line["plugin_e2e"] = plugin_block(args)
         except Exception as e:
             line["plugin_e2e"] = {"error": repr(e)}
 
@@ -804,22 +808,55 @@ def ba_block(ctx, capi, synth, args, w, h, max_corners, K, Rs, ts, verts, tris, 
                          "achieved": build_gbs, "peak": peak, "unit": "GB/s", "frac": build_gbs / peak}}
 
 
-def plugin_block(ctx, args, w, h, max_corners, dev_frames, frame_bytes, n_frames, image_of):
-    """The Analyze pass through the reference's own entry point: polychase_core.OpticalFlowThread, frames
-    handed over as host numpy arrays one request at a time (opticalflow_thread.h:50-132), SQLite database
-    written (database.cc:108-214).  Wall clock from the constructor to the terminal message."""
+def plugin_block(args):
+    """The Analyze pass through the reference's own entry point, in a fresh process like a user's (Blender's):
+    `python bench.py --plugin-only`.  (Inside this process, next to a context that holds tens of GB, creating and
+    destroying the analyze context alone costs over a second of cudaMalloc / cudaFree.)"""
+    cmd = [sys.executable, os.path.abspath(__file__), "--plugin-only", "--config", args.config, "--motion", args.motion,
+           "--plugin-frames", str(args.plugin_frames)]
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE")}
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env)
+    if out.returncode != 0:
+        return {"error": out.stderr[-500:]}
+    return json.loads(out.stdout.strip().splitlines()[-1])
+
+
+def plugin_only(args):
+    """polychase_core.OpticalFlowThread, frames handed over as host numpy arrays one request at a time
+    (opticalflow_thread.h:50-132), SQLite database written (database.cc:108-214).  Wall clock from the
+    constructor to the terminal message."""
     import ctypes
     import shutil
     import tempfile
+    from polychase_b200 import capi, synth
     from polychase_b200 import polychase_core as core
+    w, h, max_corners, _ = CONFIGS[args.config]
+    speed = synth.survey_speed(w) if args.motion == "survey" else 1.0
     F = args.plugin_frames
-    ring = min(32, n_frames)
+    ring = 32
+    ctx = capi.Context(device=0, max_width=w, max_height=h, max_features=1024)        # renders the clip, then goes away
+    ctx.synth_set_texture(synth.make_texture(w, h, seed=0))
+    K = synth.intrinsics(w, h)
+    scale = synth.plane_scale(w, 4.0)
+    Rs, ts = synth.camera_path(ring, 4.0, 0, speed)
+    dev = ctx.device_alloc(w * h * 3)
     host = []
-    for i in range(ring):                                     # host copies of the first `ring` resident frames
+    for i in range(ring):
+        ctx.synth_render(synth.homography(K, Rs[i], ts[i], w, h, scale), dev, w * 3)
+        ctx.synchronize()
         a = np.empty((h, w, 3), np.uint8)
-        ctx.lib.pc_memcpy_d2h(ctx.h, a.ctypes.data_as(ctypes.c_void_p), ctypes.c_void_p(dev_frames + i * frame_bytes),
-                              a.nbytes)
+        ctx.lib.pc_memcpy_d2h(ctx.h, a.ctypes.data_as(ctypes.c_void_p), ctypes.c_void_p(dev), a.nbytes)
         host.append(a)
+    ctx.device_free(dev)
+    ctx.close()
+
+    def image_of(idx):
+        if idx < ring:
+            return idx
+        period = 2 * (ring - 1)
+        m = idx % period
+        return m if m < ring else period - m
+
     tmp = tempfile.mkdtemp()
     try:
         dbp = os.path.join(tmp, "clip.db")
@@ -841,7 +878,7 @@ def plugin_block(ctx, args, w, h, max_corners, dev_frames, frame_bytes, n_frames
                 t1 = time.perf_counter()
                 if t_first is None:
                     t_first = t1 - t0
-                th.provide_frame(m.frame_id, host[image_of(m.frame_id - 1, ring)])
+                th.provide_frame(m.frame_id, host[image_of(m.frame_id - 1)])
                 t_last_req = time.perf_counter()
                 provide_s += t_last_req - t1
             elif isinstance(m, core.CppException):
@@ -849,12 +886,14 @@ def plugin_block(ctx, args, w, h, max_corners, dev_frames, frame_bytes, n_frames
         th.join()
         dt = time.perf_counter() - t0
         pairs = 8 * F - 30
-        return {"entry_point": "polychase_core.OpticalFlowThread (request / provide_frame hand-off) + SQLite database",
-                "frames": F, "directed_pairs": pairs, "wall_s": dt, "value": pairs / dt, "unit": "frame-pairs/s",
-                "frames_per_s": F / dt, "db_bytes": os.path.getsize(dbp), "errors": errors,
-                "breakdown_s": {"until_first_request": t_first, "inside_provide_frame": provide_s,
-                                "first_to_last_request": (t_last_req - t0 - t_first) if t_first is not None else None,
-                                "after_last_request": dt - (t_last_req - t0) if t_last_req else None}}
+        print(json.dumps({
+            "entry_point": "polychase_core.OpticalFlowThread (request / provide_frame hand-off) + SQLite database, "
+                           "fresh process",
+            "frames": F, "directed_pairs": pairs, "wall_s": dt, "value": pairs / dt, "unit": "frame-pairs/s",
+            "frames_per_s": F / dt, "db_bytes": os.path.getsize(dbp), "errors": errors,
+            "breakdown_s": {"until_first_request": t_first, "inside_provide_frame": provide_s,
+                            "first_to_last_request": (t_last_req - t0 - t_first) if t_first is not None else None,
+                            "after_last_request": dt - (t_last_req - t0) if t_last_req else None}}))
     finally:
         shutil.rmtree(tmp, ignore_errors=True)
 

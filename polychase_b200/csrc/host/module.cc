@@ -1,6 +1,6 @@
 // pybind11 module `polychase_core`: the Python surface of /root/reference/cpp/polychase_pybind.cc:29-348
-// (same class, method, argument and enum names) over the B200 host pipelines.  Interactive
-// pin mode (PinUpdate, find_transformation; pin_mode.cc) is out of scope for this path.
+// (same class, method, argument and enum names) over the B200 host pipelines, including the interactive
+// pin mode (PinUpdate, find_transformation; pin_mode.cc) whose three-and-more-pin solve runs on K11.
 #include <pybind11/functional.h>
 #include <pybind11/numpy.h>
 #include <pybind11/pybind11.h>
@@ -10,6 +10,7 @@
 #include <cstring>
 
 #include "database.h"
+#include "pin_mode.h"
 #include "pipelines.h"
 #include "threads.h"
 #include "types.h"
@@ -161,6 +162,13 @@ PYBIND11_MODULE(polychase_core, m) {
         .def_property_readonly("barycentric_coordinate", [](const RayHit& h) { return ArrToNumpy(h.barycentric_coordinate); })
         .def_readwrite("t", &RayHit::t)
         .def_readwrite("primitive_id", &RayHit::primitive_id);
+
+    py::class_<PinUpdate>(m, "PinUpdate")                                   // polychase_pybind.cc:65-69
+        .def(py::init([](uint32_t pin_idx, const FArr& pos) { return PinUpdate{pin_idx, ArrFromNumpy<2>(pos)}; }),
+             py::arg("pin_idx"), py::arg("pin_pos"))
+        .def_readwrite("pin_idx", &PinUpdate::pin_idx)
+        .def_property("pos", [](const PinUpdate& u) { return ArrToNumpy(u.pos); },
+                      [](PinUpdate& u, const FArr& a) { u.pos = ArrFromNumpy<2>(a); });
 
     py::class_<ImagePairFlow>(m, "ImagePairFlow")
         .def(py::init<>())
@@ -361,6 +369,20 @@ PYBIND11_MODULE(polychase_core, m) {
               return mesh.RayCast(scene, p, check_mask);
           },
           py::arg("accel_mesh"), py::arg("scene_transform"), py::arg("pos"), py::arg("check_mask"));
+
+    m.def("find_transformation",                                            // polychase_pybind.cc:319-325
+          [](const FArr& object_points, const SceneTransformations& initial, const SceneTransformations& current,
+             const PinUpdate& update, TransformationType trans_type, bool of, bool opp) {
+              if (object_points.ndim() != 2 || object_points.shape(1) != 3)
+                  throw std::invalid_argument("object_points: expected an (N, 3) float32 array");
+              std::vector<float> pts((size_t)object_points.size());
+              if (!pts.empty()) memcpy(pts.data(), object_points.data(), pts.size() * sizeof(float));
+              py::gil_scoped_release release;
+              return FindTransformation(pts, initial, current, update, trans_type, of, opp);
+          },
+          py::arg("object_points"), py::arg("initial_scene_transform"), py::arg("current_scene_transform"),
+          py::arg("update"), py::arg("trans_type"), py::arg("optimize_focal_length") = false,
+          py::arg("optimize_principal_point") = false);
 
     m.def("generate_optical_flow_database",
           [](const VideoInfo& vi, py::function accessor, py::object callback, const std::string& path,

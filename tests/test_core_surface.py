@@ -22,7 +22,8 @@ def test_surface_names(core):
                  "OpticalFlowRequest", "OpticalFlowThread", "TransformationType", "CameraConvention",
                  "CameraIntrinsics", "Pose", "CameraState", "LossType", "BundleOptions", "BundleStats", "PnPResult",
                  "FrameTrackingResult", "CameraTrajectory", "RefineTrajectoryUpdate", "CppException", "ray_cast",
-                 "generate_optical_flow_database", "track_sequence", "refine_trajectory"):
+                 "generate_optical_flow_database", "track_sequence", "refine_trajectory", "PinUpdate",
+                 "find_transformation"):
         assert hasattr(core, name), name
 
 
@@ -127,3 +128,78 @@ def test_empty_blobs_round_trip(core, tmp_path):
     d.write_image_pair_flow(1, 2, np.zeros(0, np.uint32), np.zeros((0, 2), np.float32), np.zeros(0, np.float32))
     assert d.read_keypoints(1).shape == (0, 2)
     assert len(d.read_image_pair_flow(1, 2).src_kps_indices) == 0
+
+
+def _scene(core, conv_gl=True):
+    w, h, f = 640.0, 480.0, 700.0
+    if conv_gl:      # the addon's camera: OpenGL, negated fx / fy (blender_addon/core.py:348-357)
+        intr = core.CameraIntrinsics(-f, -f, w / 2, h / 2, 1.0, w, h, core.CameraConvention.OpenGL)
+        view = np.diag([1.0, -1.0, -1.0, 1.0]).astype(np.float32)
+    else:
+        intr = core.CameraIntrinsics(f, f, w / 2, h / 2, 1.0, w, h, core.CameraConvention.OpenCV)
+        view = np.eye(4, dtype=np.float32)
+    view[:3, 3] = view[:3, :3] @ np.array([0.1, -0.2, 5.0], np.float32)
+    model = np.eye(4, dtype=np.float32)
+    model[:3, 3] = [0.3, 0.1, 0.2]
+    return core.SceneTransformations(model, view, intr)
+
+
+def _project(scene, pts):
+    mv = np.asarray(scene.view_matrix, np.float64) @ np.asarray(scene.model_matrix, np.float64)
+    pc = pts @ mv[:3, :3].T + mv[:3, 3]
+    k = scene.intrinsics
+    return np.stack([k.fx * pc[:, 0] / pc[:, 2] + k.cx, k.fy * pc[:, 1] / pc[:, 2] + k.cy], 1)
+
+
+def _two_pin_restatement(scene, pts, pin, pos, trans):
+    """FindTransformation2 (pin_mode.cc:151-217) written independently in float64 numpy."""
+    M, V, k = np.asarray(scene.model_matrix, np.float64), np.asarray(scene.view_matrix, np.float64), scene.intrinsics
+    Vi = np.linalg.inv(V)
+    s = 1.0 if k.convention.name == "OpenCV" else -1.0
+    d = Vi[:3, :3] @ (s * np.array([(pos[0] - k.cx) / k.fx, (pos[1] - k.cy) / k.fy, 1.0]))
+    o = Vi[:3, 3]
+    moving = M[:3, :3] @ pts[pin] + M[:3, 3]
+    anchor = M[:3, :3] @ pts[1 - pin] + M[:3, 3]
+    depth = np.linalg.norm(moving - o)
+    tm = o + depth * d / np.linalg.norm(d)
+    du, dv = moving - anchor, tm - anchor
+    dn = Vi[:3, 2] / np.linalg.norm(Vi[:3, 2])
+    duu, dvu = du / np.linalg.norm(du), dv / np.linalg.norm(dv)
+    ang = np.arctan2(np.cross(duu, dvu) @ dn, duu @ dvu)
+    Kx = np.array([[0, -dn[2], dn[1]], [dn[2], 0, -dn[0]], [-dn[1], dn[0], 0]])
+    R = np.eye(3) + np.sin(ang) * Kx + (1 - np.cos(ang)) * Kx @ Kx
+    new_anchor = o + (anchor - o) * (np.linalg.norm(du) / np.linalg.norm(dv))
+    U = np.eye(4)
+    U[:3, :3] = R
+    U[:3, 3] = new_anchor - R @ anchor
+    return (U @ M, V) if trans == "Model" else (M, V @ U)
+
+
+@pytest.mark.parametrize("conv_gl", [True, False])
+@pytest.mark.parametrize("trans", ["Model", "Camera"])
+def test_find_transformation_one_and_two_pins(core, conv_gl, trans):
+    """FindTransformation1 / FindTransformation2 (pin_mode.cc:110-217) are closed-form host math: after the update the
+    dragged pin projects onto the cursor; with two pins the anchor keeps its projection.  No kernel is launched."""
+    scene = _scene(core, conv_gl)
+    tt = getattr(core.TransformationType, trans)
+    pts = np.array([[0.2, -0.1, 0.3], [-0.4, 0.25, -0.1]], np.float32)
+    before = _project(scene, pts.astype(np.float64))
+    target = before[0] + np.array([23.0, -11.0])
+    out = core.find_transformation(pts[:1], scene, scene, core.PinUpdate(0, target.astype(np.float32)), tt)
+    assert np.abs(_project(out, pts[:1].astype(np.float64))[0] - target).max() < 2e-2
+    if trans == "Model":
+        assert np.array_equal(out.view_matrix, scene.view_matrix)
+        assert np.allclose(np.asarray(out.model_matrix)[:3, :3], np.asarray(scene.model_matrix)[:3, :3])   # pure translation
+    else:
+        assert np.array_equal(out.model_matrix, scene.model_matrix)
+    out2 = core.find_transformation(pts, scene, scene, core.PinUpdate(0, target.astype(np.float32)), tt)
+    after = _project(out2, pts.astype(np.float64))
+    # two pins: rotation about the view axis through the anchor + a scale expressed as moving the anchor along its
+    # view ray -- the reference's own approximation (its FIXME, pin_mode.cc:186-191): the dragged pin goes most of the
+    # way, the anchor keeps its projection exactly
+    assert np.linalg.norm(after[0] - target) < 0.4 * np.linalg.norm(target - before[0])
+    assert np.abs(after[1] - before[1]).max() < 2e-2
+    want_model, want_view = _two_pin_restatement(scene, pts.astype(np.float64), 0, target, trans)
+    assert np.allclose(out2.model_matrix, want_model, atol=2e-5) and np.allclose(out2.view_matrix, want_view, atol=2e-5)
+    with pytest.raises(Exception):                        # CHECK_LT(update.pin_idx, object_points.rows())
+        core.find_transformation(pts, scene, scene, core.PinUpdate(2, target.astype(np.float32)), tt)

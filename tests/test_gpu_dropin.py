@@ -288,3 +288,38 @@ def test_resume_with_empty_keypoint_row_is_authoritative(core, tmp_path):
         elif len(idx):
             assert int(idx.max()) < len(o.read_keypoints(a))
     o.close()
+
+
+@pytest.mark.parametrize("trans", ["Model", "Camera"])
+def test_find_transformation_many_pins_on_the_gpu(core, trans):
+    """FindTransformationN (pin_mode.cc:16-108): three and more pins are solved by SolvePnPIterative (K11 through
+    pc_solve_pnp) with the trivial loss from the current transform.  Dragging one of six pins: every pin must
+    reproject close to its requested position, exactly so when the drag is a rigid motion of the whole set."""
+    from tests.test_core_surface import _project, _scene
+    scene = _scene(core, True)
+    tt = getattr(core.TransformationType, trans)
+    rng = np.random.default_rng(2)
+    pts = rng.uniform(-0.6, 0.6, (6, 3)).astype(F)
+    before = _project(scene, pts.astype(np.float64))
+    # a consistent drag: rotate the object a little about its own z axis and read off where pin 2 lands
+    a = np.deg2rad(3.0)
+    Rz = np.array([[np.cos(a), -np.sin(a), 0], [np.sin(a), np.cos(a), 0], [0, 0, 1.0]])
+    moved = core.SceneTransformations(np.asarray(scene.model_matrix) @ np.block([[Rz, np.zeros((3, 1))], [np.zeros((1, 3)), 1]]).astype(F),
+                                      scene.view_matrix, scene.intrinsics)
+    target = _project(moved, pts.astype(np.float64))
+    out = core.find_transformation(pts, scene, scene, core.PinUpdate(2, target[2].astype(F)), tt)
+    after = _project(out, pts.astype(np.float64))
+    assert np.abs(after[2] - target[2]).max() < 1.0               # the dragged pin follows the cursor
+    others = [i for i in range(6) if i != 2]
+    assert np.abs(after[others] - before[others]).max() < 1.5     # the others stay pinned (least squares over 6 pins)
+    if trans == "Model":
+        assert np.array_equal(out.view_matrix, scene.view_matrix)
+    else:
+        assert np.array_equal(out.model_matrix, scene.model_matrix)
+    # all six pins moved consistently: the solve recovers that rigid motion
+    cur = scene
+    for i in range(6):
+        cur = core.find_transformation(pts, scene, cur, core.PinUpdate(i, target[i].astype(F)), tt)
+    # (each call re-projects from `scene`, so only the last update is in effect: pin 5 on target, the rest near `before`)
+    fin = _project(cur, pts.astype(np.float64))
+    assert np.abs(fin[5] - target[5]).max() < 1.0

@@ -364,8 +364,12 @@ def check_cost_and_normal_equations(ctx, scene, opt_f, opt_pp, loss, seed=3):
         np.fill_diagonal(Ad, dg * (1.0 + lam))
         want_step = -np.linalg.solve(Ad, jtr.astype(np.float64))
         got_step, got_norm = ctx.ba_solve_step(lam)
-        assert np.abs(got_step - want_step).max() <= 2e-3 * np.abs(want_step).max(), lam
-        assert abs(got_norm - np.linalg.norm(want_step)) <= 2e-3 * np.linalg.norm(want_step)
+        # a float32 Cholesky is backward stable: the residual is small against |A| |x| + |b| whatever the conditioning
+        # (with the intrinsics free the system is ill conditioned and the forward error alone says little)
+        resid = Ad @ got_step.astype(np.float64) + jtr
+        assert np.abs(resid).max() <= 2e-5 * (np.abs(Ad) @ np.abs(got_step) + np.abs(jtr)).max(), lam
+        assert np.abs(got_step - want_step).max() <= (2e-3 if p == 6 else 5e-2) * np.abs(want_step).max(), lam
+        assert abs(got_norm - np.linalg.norm(got_step.astype(np.float64))) <= 1e-5 * got_norm
     return prob
 
 
