@@ -145,12 +145,19 @@ static int build_pyramid(pc_ctx* c, FrameSlot* f, const uint8_t* img_dev, size_t
     f->h = h;
     f->levels = plan_levels(f, w, h, fo->window_size, fo->max_level);
     span_begin(c, KF_GRAY_PYR, s);
-    if (channels == 3) launch_rgb_to_gray(img_dev, stride, f->level[0], s);
-    else launch_copy_gray(img_dev, stride, f->level[0], s);
-    for (int L = 1; L < f->levels; L++) launch_pyr_down(f->level[L - 1], f->level[L], s);
+    int done = 0, n_launch = 0;
+    static const bool no_tma = getenv("PC_NO_TMA_PYRAMID") != nullptr;
+    if (channels == 3 && !no_tma) done = launch_pyramid_tma(img_dev, stride, f->level, f->levels, s, &n_launch);
+    if (done == 0) {
+        if (channels == 3) launch_rgb_to_gray(img_dev, stride, f->level[0], s);
+        else launch_copy_gray(img_dev, stride, f->level[0], s);
+        done = 1;
+        n_launch += 1 + (channels == 3 && (w % 16) ? 1 : 0);
+    }
+    for (int L = done; L < f->levels; L++, n_launch++) launch_pyr_down(f->level[L - 1], f->level[L], s);
     launch_pad_border(f->level, f->levels, s);
     span_end(c, s);
-    return check_launch(c, "gray+pyramid", f->levels + 1 + (channels == 3 && (w % 16) ? 1 : 0));
+    return check_launch(c, "gray+pyramid", n_launch + 1);
 }
 
 static int run_detector(pc_ctx* c, FrameSlot* f, const pc_gftt_opts* go, cudaStream_t s) {

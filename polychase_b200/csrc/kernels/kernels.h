@@ -30,6 +30,9 @@ struct PyramidView {     // what the LK kernel sees of one frame
 void launch_rgb_to_gray(const uint8_t* rgb, size_t stride, Image8 gray, cudaStream_t s);
 void launch_copy_gray(const uint8_t* src, size_t stride, Image8 gray, cudaStream_t s);
 void launch_pyr_down(Image8 src, Image8 dst, cudaStream_t s);
+// Fused TMA path (pyramid_tma.cu): gray + levels 1..3 from an RGB8 device image in two launches.  Returns how many
+// levels of `lv` it wrote (0 = not applicable: nothing launched, use the kernels above); *launches = kernels launched.
+int launch_pyramid_tma(const uint8_t* rgb, size_t stride, const Image8* lv, int levels, cudaStream_t s, int* launches);
 // Fills the apron (kPadX / kPadY, BORDER_REFLECT_101) of `levels` planes in one launch.
 void launch_pad_border(const Image8* planes, int levels, cudaStream_t s);
 

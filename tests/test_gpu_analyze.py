@@ -13,7 +13,11 @@ def _u32(a):
     return np.ascontiguousarray(a).view(np.uint32)
 
 
-@pytest.mark.parametrize("w,h", [(640, 480), (643, 487), (1280, 720), (100, 75)])
+# (640, 480) .. (1916, 1082): the fused TMA path (pyramid_tma.cu: width a multiple of 4), with edge tiles of every
+# kind -- widths / heights that are not multiples of the 128 x 32 block, odd level sizes, a single tile row;
+# (643, 487), (100, 75): the generic kernels (gray_pyr.cu)
+@pytest.mark.parametrize("w,h", [(640, 480), (643, 487), (1280, 720), (100, 75), (644, 483), (1284, 722), (1916, 1082),
+                                 (300, 37), (136, 35), (292, 90)])
 def test_gray_pyramid_bit_exact(ctx_small, w, h):
     rng = np.random.default_rng(w * 7 + h)
     rgb = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
