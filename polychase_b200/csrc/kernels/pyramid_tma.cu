@@ -13,6 +13,9 @@
 //   l2_l3_tma_kernel     one CTA per 32 x 8 tile of level 3: a 144 x 43 patch of level 1 by TMA, the 68 x 20
 //                        region of level 2 over it (its 64 x 16 centre is stored), then the level-3 tile.
 // REFLECT_101 is applied when the patch is read in shared memory, by edge CTAs only.
+// TMA boxes must start on a 16-byte boundary of the innermost dimension (an unaligned inner coordinate raises an
+// illegal-instruction fault on sm_100: scripts/probes/tma_probe.cu), so both load boxes start a few bytes left of
+// the patch (A_RGB_SKIP / B_P1_SKIP); rows are unconstrained.
 // Algorithmic bytes per 4K frame: 24.9 MB RGB read + 11.0 MB pyramid written; the RGB halo re-reads (16 %) and
 // the level-1 patch re-reads hit L2.
 #include <cuda.h>
@@ -78,7 +81,8 @@ __device__ __forceinline__ uint32_t gray_of(uint32_t r, uint32_t g, uint32_t b) 
 constexpr int A_TW = 64, A_TH = 16;              // level-1 tile
 constexpr int A_IW = 2 * A_TW + 8;               // 136 level-0 columns under it (origin 4 left of the block: word aligned)
 constexpr int A_IH = 2 * A_TH + 3;               // 35 rows
-constexpr int A_RGB_ROW = 416;                   // 3 * 136 = 408 bytes per patch row, rounded to the 16-byte box granularity
+constexpr int A_RGB_ROW = 416;                   // box row: 4 skipped bytes + 3 * 136 = 408, rounded to the 16-byte box granularity
+constexpr int A_RGB_SKIP = 4;                    // the box starts at byte 384 bx - 16 (16-byte aligned), the patch at 384 bx - 12
 constexpr int A_THREADS = 256;
 
 struct SmemA {
@@ -101,7 +105,7 @@ __global__ void __launch_bounds__(A_THREADS) gray_l1_tma_kernel(const __grid_con
     __syncthreads();
     if (tid == 0) {
         mbar_expect_tx(&S.bar, A_IH * A_RGB_ROW);
-        tma_load_2d(&S.rgb[0][0], &tm_rgb, (3 * ax0) / 4, ay0, &S.bar);   // x in 4-byte elements: 96 bx - 3
+        tma_load_2d(&S.rgb[0][0], &tm_rgb, (3 * ax0 - A_RGB_SKIP) / 4, ay0, &S.bar);   // x in 4-byte elements: 96 bx - 4
     }
     mbar_wait(&S.bar, 0);
     // gray of the whole patch, four pixels (12 bytes = 3 words) per step; edge CTAs read through REFLECT_101
@@ -111,7 +115,7 @@ __global__ void __launch_bounds__(A_THREADS) gray_l1_tma_kernel(const __grid_con
         const int r = idx / GPR, g = idx - r * GPR;
         uint32_t out;
         if (!edge) {
-            const uint32_t* p = reinterpret_cast<const uint32_t*>(&S.rgb[r][12 * g]);
+            const uint32_t* p = reinterpret_cast<const uint32_t*>(&S.rgb[r][A_RGB_SKIP + 12 * g]);
             const uint32_t a = p[0], b = p[1], c = p[2];
             const uint32_t p0 = gray_of(a & 255u, (a >> 8) & 255u, (a >> 16) & 255u);
             const uint32_t p1 = gray_of(a >> 24, b & 255u, (b >> 8) & 255u);
@@ -125,7 +129,7 @@ __global__ void __launch_bounds__(A_THREADS) gray_l1_tma_kernel(const __grid_con
 #pragma unroll
             for (int k = 0; k < 4; k++) {
                 const int sc = clampi(reflect101(ax0 + 4 * g + k, w) - ax0, 0, A_IW - 1);
-                const uint8_t* q = &S.rgb[sr][3 * sc];
+                const uint8_t* q = &S.rgb[sr][A_RGB_SKIP + 3 * sc];
                 out |= gray_of(q[0], q[1], q[2]) << (8 * k);
             }
         }
@@ -164,7 +168,8 @@ __global__ void __launch_bounds__(A_THREADS) gray_l1_tma_kernel(const __grid_con
 constexpr int B_T3W = 32, B_T3H = 8;             // level-3 tile
 constexpr int B_R2W = 2 * B_T3W + 4;             // 68 x 20 region of level 2 (its 64 x 16 centre is owned)
 constexpr int B_R2H = 2 * B_T3H + 4;
-constexpr int B_P1W = 144;                       // level-1 patch: 2 * 68 + 4 = 140 columns, padded to a 16-byte multiple
+constexpr int B_P1W = 160;                       // box row: 10 skipped bytes + the 140-column level-1 patch (2 * 68 + 4), rounded to 16
+constexpr int B_P1_SKIP = 10;                    // the box starts at x = 128 bx - 16, the patch at 128 bx - 6
 constexpr int B_P1H = 2 * B_R2H + 3;             // 43 rows
 constexpr int B_THREADS = 256;
 
@@ -190,22 +195,22 @@ __global__ void __launch_bounds__(B_THREADS) l2_l3_tma_kernel(const __grid_const
     __syncthreads();
     if (tid == 0) {
         mbar_expect_tx(&S.bar, B_P1H * B_P1W);
-        tma_load_2d(&S.l1[0][0], &tm_l1, x1_0, y1_0, &S.bar);
+        tma_load_2d(&S.l1[0][0], &tm_l1, x1_0 - B_P1_SKIP, y1_0, &S.bar);
     }
     mbar_wait(&S.bar, 0);
-    const bool edge = x1_0 < 0 || y1_0 < 0 || x1_0 + B_P1W > w1 || y1_0 + B_P1H > h1;
+    const bool edge = x1_0 < 0 || y1_0 < 0 || x1_0 + 2 * B_R2W + 4 > w1 || y1_0 + B_P1H > h1;
     // horizontal pass of level 1 -> level 2: region column c is level-2 x = x2_0 + c (REFLECT_101 in level 2)
     for (int idx = tid; idx < B_P1H * B_R2W; idx += B_THREADS) {
         const int r = idx / B_R2W, c = idx - r * B_R2W;
         uint32_t s;
         if (!edge) {
-            const uint8_t* t = &S.l1[r][2 * c];
+            const uint8_t* t = &S.l1[r][B_P1_SKIP + 2 * c];
             s = t[0] + 4 * t[1] + 6 * t[2] + 4 * t[3] + t[4];
         } else {
             // patch row r stands for level-1 row y1_0 + r of the *mapped* level-2 row; rows are mapped in the vertical pass
             const int x2 = reflect101(x2_0 + c, w2);
-            const uint8_t* row = S.l1[r];
-            auto col = [&](int x1) { return clampi(reflect101(x1, w1) - x1_0, 0, B_P1W - 1); };
+            const uint8_t* row = S.l1[r] + B_P1_SKIP;
+            auto col = [&](int x1) { return clampi(reflect101(x1, w1) - x1_0, 0, B_P1W - B_P1_SKIP - 1); };
             s = row[col(2 * x2 - 2)] + 4 * row[col(2 * x2 - 1)] + 6 * row[col(2 * x2)] + 4 * row[col(2 * x2 + 1)] +
                 row[col(2 * x2 + 2)];
         }

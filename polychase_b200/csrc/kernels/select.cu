@@ -244,9 +244,23 @@ __device__ __forceinline__ int suffix_threshold_bin(const int* hist, int want, i
     return s_res[3];
 }
 
+// The barrier between the rounds of the fixed point: the whole (cooperative) grid, or -- with max_corners > 0, where a
+// few thousand strong candidates decide everything -- one thread-block cluster.  A cooperative launch needs every one
+// of its 2 x 148 blocks resident at the same time, so in the pipeline it waits for blocks of the concurrent LK batch
+// to retire on ALL SMs while its early blocks spin at the barrier (measured: 0.21 ms per frame in the pipeline against
+// 0.03 ms alone); a 16-CTA cluster needs 16 free slots in one GPC and leaves the rest of the chip to LK.
+template <bool CLUSTER>
+struct RoundBarrier {
+    __device__ __forceinline__ void sync() {
+        if (CLUSTER) cg::this_cluster().sync();
+        else cg::this_grid().sync();
+    }
+};
+
 // One fixed-point run over list[0..n): returns the number of candidates still undecided (0 =
-// converged).  Every block of the grid must call it (grid barrier per round).
-__device__ __forceinline__ int greedy_rounds(cg::grid_group& grid, int* block_undecided,
+// converged).  Every block of the grid must call it (barrier per round).
+template <bool CLUSTER>
+__device__ __forceinline__ int greedy_rounds(RoundBarrier<CLUSTER>& grid, int* block_undecided,
                                              const unsigned long long* __restrict__ list, int n,
                                              const float* __restrict__ eig, int eig_pitch, uint8_t* state,
                                              int state_pitch, int w, int h, int R, double md2,
@@ -330,13 +344,14 @@ __device__ __forceinline__ int greedy_rounds(cg::grid_group& grid, int* block_un
 //   8 466 candidates give 8 000 kept corners at 4K), then the band down to 4 x max_corners, then
 //   everything, stopping as soon as max_corners corners are kept.  Every block recomputes the bins
 //   (4096 ints); each stage appends its band of the candidate list to `strong`.
+template <bool CLUSTER>
 __global__ void __launch_bounds__(256) greedy_suppress_kernel(
     const unsigned long long* __restrict__ cand, const int* __restrict__ cand_count, int cand_cap,
     const float* __restrict__ eig, int eig_pitch, uint8_t* state, int state_pitch, int w, int h, int R,
     double md2, unsigned long long* __restrict__ accepted, int* accepted_count, int* kept_hist, int* round_counters,
     int* remaining, const int* value_hist, unsigned long long* __restrict__ strong, int* strong_count,
     int max_corners) {
-    cg::grid_group grid = cg::this_grid();
+    RoundBarrier<CLUSTER> grid;
     __shared__ int block_undecided;
     __shared__ int s_warp[8], s_res[8];
     const int n = min(*cand_count, cand_cap);
@@ -540,7 +555,7 @@ static void launch_greedy(const unsigned long long* cand, const int* cand_count,
     double md2 = min_distance * min_distance;
     static int blocks_per_sm = 0;
     if (!blocks_per_sm) {
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, greedy_suppress_kernel, 256, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, greedy_suppress_kernel<false>, 256, 0);
         blocks_per_sm = std::min(std::max(blocks_per_sm, 1), 2);
     }
     int nblocks = sm_count * blocks_per_sm;
@@ -548,11 +563,55 @@ static void launch_greedy(const unsigned long long* cand, const int* cand_count,
     unsigned long long* strong = ws.strong;
     int* strong_count = ws.sel + 1;
     int* round_counters = ws.round_counters;
+    // max_corners > 0: one 16-CTA cluster (8 where 16 cannot be placed); PC_GREEDY_GRID=1 forces the cooperative grid
+    static int cluster = -1;
+    if (cluster < 0) {
+        cluster = 0;
+        if (!getenv("PC_GREEDY_GRID")) {
+            int want = 16;
+            if (cudaFuncSetAttribute(greedy_suppress_kernel<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
+                cudaGetLastError();
+                want = 8;
+            }
+            for (; want >= 8 && !cluster; want -= 8) {
+                cudaLaunchConfig_t cfg = {};
+                cfg.gridDim = dim3(want);
+                cfg.blockDim = dim3(256);
+                cudaLaunchAttribute attr[1];
+                attr[0].id = cudaLaunchAttributeClusterDimension;
+                attr[0].val.clusterDim.x = want;
+                attr[0].val.clusterDim.y = 1;
+                attr[0].val.clusterDim.z = 1;
+                cfg.attrs = attr;
+                cfg.numAttrs = 1;
+                int n = 0;
+                if (cudaOccupancyMaxActiveClusters(&n, greedy_suppress_kernel<true>, &cfg) == cudaSuccess && n >= 1) cluster = want;
+                else cudaGetLastError();
+            }
+        }
+    }
+    if (max_corners > 0 && cluster > 0) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(cluster);
+        cfg.blockDim = dim3(256);
+        cfg.stream = s;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = cluster;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        cudaLaunchKernelEx(&cfg, greedy_suppress_kernel<true>, cand, cand_count, cand_cap, eig, eig_pitch, state, state_pitch, w,
+                           h, R, md2, ws.accepted, ws.accepted_count, kept_hist, round_counters, ws.remaining, value_hist,
+                           strong, strong_count, max_corners);
+        return;
+    }
     void* args[] = {(void*)&cand, (void*)&cand_count, (void*)&cand_cap, (void*)&eig, (void*)&eig_pitch, (void*)&state,
                     (void*)&state_pitch, (void*)&w, (void*)&h, (void*)&R, (void*)&md2, (void*)&ws.accepted,
                     (void*)&ws.accepted_count, (void*)&kept_hist, (void*)&round_counters, (void*)&ws.remaining,
                     (void*)&value_hist, (void*)&strong, (void*)&strong_count, (void*)&max_corners};
-    cudaLaunchCooperativeKernel((void*)greedy_suppress_kernel, dim3(nblocks), dim3(256), args, 0, s);
+    cudaLaunchCooperativeKernel((void*)greedy_suppress_kernel<false>, dim3(nblocks), dim3(256), args, 0, s);
 }
 
 void launch_select(const unsigned long long* cand, const int* cand_count, int cand_cap, const float* eig,
