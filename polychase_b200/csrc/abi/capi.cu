@@ -320,6 +320,11 @@ pc_ctx::~pc_ctx() {
     if (side) cudaStreamDestroy(side);
     if (compute) cudaStreamDestroy(compute);
     if (h2d) cudaStreamDestroy(h2d);
+    for (int k = 0; k < 3; k++) {
+        if (h2d_extra[k]) cudaStreamDestroy(h2d_extra[k]);
+        if (h2d_extra_ev[k]) cudaEventDestroy(h2d_extra_ev[k]);
+    }
+    if (h2d_fork) cudaEventDestroy(h2d_fork);
     if (d2h) cudaStreamDestroy(d2h);
     if (d2h_rows) cudaStreamDestroy(d2h_rows);
 }
@@ -392,6 +397,7 @@ int pc_create(const pc_limits* limits, pc_ctx** out) {
         if (!e || atoi(e) != 0) PC_CUDA(nullptr, cudaStreamCreateWithPriority(&cp->side, cudaStreamNonBlocking, lo));
     }
     PC_CUDA(nullptr, cudaStreamCreateWithFlags(&cp->h2d, cudaStreamNonBlocking));
+    PC_CUDA(nullptr, cudaEventCreateWithFlags(&cp->h2d_fork, cudaEventDisableTiming));
     PC_CUDA(nullptr, cudaStreamCreateWithFlags(&cp->d2h, cudaStreamNonBlocking));
     PC_CUDA(nullptr, cudaStreamCreateWithFlags(&cp->d2h_rows, cudaStreamNonBlocking));
 
@@ -920,7 +926,30 @@ int pc_analyze_push_frame(pc_ctx* c, int32_t frame_id, const uint8_t* rgb, size_
         }
         // the staging buffer's previous contents must have been consumed by its gray kernel
         if (st.gray_pending) PC_CUDA(c, cudaStreamWaitEvent(c->h2d, st.gray_done, 0));
-        PC_CUDA(c, cudaMemcpyAsync(st.rgb_dev, rgb, bytes, cudaMemcpyHostToDevice, c->h2d));
+        // PC_H2D_SPLIT=n (2..4): the frame travels as n slices on n streams, i.e. on several copy engines at once
+        static const int split = [] { const char* e = getenv("PC_H2D_SPLIT"); return e ? std::min(std::max(atoi(e), 1), 4) : 1; }();
+        if (split > 1 && mem_kind == PC_MEM_HOST_PINNED) {
+            if (!c->h2d_extra[0])
+                for (int k = 0; k < 3; k++) {
+                    PC_CUDA(c, cudaStreamCreateWithFlags(&c->h2d_extra[k], cudaStreamNonBlocking));
+                    PC_CUDA(c, cudaEventCreateWithFlags(&c->h2d_extra_ev[k], cudaEventDisableTiming));
+                }
+            PC_CUDA(c, cudaEventRecord(c->h2d_fork, c->h2d));                 // the slices wait for what the h2d stream waited for
+            const size_t rows_per = ((size_t)h + split - 1) / split;
+            for (int k = 0; k < split; k++) {
+                const size_t r0 = k * rows_per, r1 = std::min((size_t)h, r0 + rows_per);
+                if (r0 >= r1) break;
+                cudaStream_t sk = k == 0 ? c->h2d : c->h2d_extra[k - 1];
+                if (k > 0) PC_CUDA(c, cudaStreamWaitEvent(sk, c->h2d_fork, 0));
+                PC_CUDA(c, cudaMemcpyAsync(st.rgb_dev + r0 * stride, rgb + r0 * stride, (r1 - r0) * stride, cudaMemcpyHostToDevice, sk));
+                if (k > 0) {
+                    PC_CUDA(c, cudaEventRecord(c->h2d_extra_ev[k - 1], sk));
+                    PC_CUDA(c, cudaStreamWaitEvent(c->h2d, c->h2d_extra_ev[k - 1], 0));
+                }
+            }
+        } else {
+            PC_CUDA(c, cudaMemcpyAsync(st.rgb_dev, rgb, bytes, cudaMemcpyHostToDevice, c->h2d));
+        }
         PC_CUDA(c, cudaEventRecord(st.uploaded, c->h2d));
         PC_CUDA(c, cudaStreamWaitEvent(c->compute, st.uploaded, 0));
         dev = st.rgb_dev;
@@ -1066,7 +1095,10 @@ int pc_device_free(pc_ctx* c, void* p) {
 }
 int pc_host_alloc_pinned(pc_ctx* c, size_t bytes, void** out) {
     PC_CUDA(c, cudaSetDevice(c->device));
-    PC_CUDA(c, cudaMallocHost(out, bytes));
+    // PC_PINNED_WC=1: write-combined page-locked memory (frames are written once by the host and only read by the
+    // copy engine; write-combined pages are not snooped during the transfer)
+    static const bool wc = getenv("PC_PINNED_WC") != nullptr && atoi(getenv("PC_PINNED_WC")) != 0;
+    PC_CUDA(c, cudaHostAlloc(out, bytes, wc ? cudaHostAllocWriteCombined : cudaHostAllocDefault));
     return PC_OK;
 }
 int pc_host_free_pinned(pc_ctx* c, void* p) {

@@ -108,6 +108,9 @@ struct pc_ctx {
     int sm_count = 0;
     cudaStream_t compute = nullptr, h2d = nullptr, d2h = nullptr;
     cudaStream_t d2h_rows = nullptr;     // pop-time row downloads: never queued behind a later frame's counts
+    cudaStream_t h2d_extra[3] = {nullptr, nullptr, nullptr};   // PC_H2D_SPLIT: extra upload streams (frame slices)
+    cudaEvent_t h2d_extra_ev[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t h2d_fork = nullptr;
     bool download_hint = false;          // the last pop asked for rows: queue the next frames' rows with their counts
     // streaming analyzer: LK batches run on this low-priority stream next to the following frame's
     // pyramid + detector on `compute` (nullptr = everything on `compute`)
