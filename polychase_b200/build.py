@@ -25,7 +25,7 @@ ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-fvisibility=hidden,-Wall,-Wno-unused-function",
           "--expt-relaxed-constexpr", "-Xptxas", "-v"]
 # files whose float arithmetic must match the CPU reference bit for bit: no implicit FMA
-NO_FMAD = {"lk.cu", "lk10.cu", "mineig.cu"}
+NO_FMAD = {"lk.cu", "lk10.cu", "lk10q.cu", "mineig.cu"}
 
 
 def sources():

@@ -203,7 +203,7 @@ static void fill_pair(pc_ctx* c, LKPair& p, const FrameSlot& a, const FrameSlot&
     p.a = view_of(a);
     p.b = view_of(b);
     p.tmpl = LKTemplates{nullptr, nullptr, 0};
-    if (use_templates && a.has_tmpl) p.tmpl = LKTemplates{a.tmpl, a.tmpl_sums, cap};
+    if (use_templates && a.has_tmpl) p.tmpl = LKTemplates{a.tmpl, a.tmpl_queue_layout ? nullptr : a.tmpl_sums, cap};
     p.pts = a.kps;
     p.n_pts = a.n_kps;
     p.next = c->lk_next + (size_t)k * cap * 2;
@@ -291,7 +291,7 @@ pc_ctx::~pc_ctx() {
     }
     cudaFree(eig); cudaFree(state); cudaFree(cell_max); cudaFree(cand); cudaFree(det_zero);
     cudaFree(sel.accepted); cudaFree(sel.sorted); cudaFree(sel.cub_temp); cudaFree(sel.strong); cudaFree(sel.bin_start);
-    cudaFree(lk_next); cudaFree(lk_status); cudaFree(lk_err);
+    cudaFree(lk_next); cudaFree(lk_status); cudaFree(lk_err); cudaFree(lk_queue);
     free_pair_out(sync_out, false);
     cudaFree(rgb_scratch);
     for (auto& st : stages) {
@@ -463,6 +463,10 @@ int pc_create(const pc_limits* limits, pc_ctx** out) {
     PC_CUDA(nullptr, cudaMalloc(&cp->lk_next, sizeof(float) * 2 * (size_t)cap * 8));
     PC_CUDA(nullptr, cudaMalloc(&cp->lk_status, (size_t)cap * 8));
     PC_CUDA(nullptr, cudaMalloc(&cp->lk_err, sizeof(float) * (size_t)cap * 8));
+    PC_CUDA(nullptr, cudaMalloc(&cp->lk_queue, sizeof(int) * 4));
+    PC_CUDA(nullptr, cudaMemset(cp->lk_queue, 0, sizeof(int) * 4));
+    if (const char* e = getenv("PC_LK_QUEUE")) cp->lk_queue_mode = atoi(e) != 0;
+    if (const char* e = getenv("PC_LK_BUDGET")) cp->lk_queue_budget = std::max(0, atoi(e));
     int rc = alloc_pair_out(nullptr, cp->sync_out, cap, false);
     if (rc) return rc;
     *out = c.release();
@@ -736,7 +740,8 @@ int pc_analyze_begin(pc_ctx* c, const pc_video_info* vi, const pc_gftt_opts* go,
     // long as it stays under 4 GB for the whole ring (the kernel computes templates itself otherwise)
     {
         const int tl = std::min(std::max(fo->max_level, 0) + 1, kMaxLevels);
-        const size_t per_slot = (size_t)tl * c->lim.max_features * kLkTemplateBytesPerPoint;
+        const size_t per_slot = (size_t)tl * c->lim.max_features *
+                                (c->lk_queue_mode ? kLkQueueTemplateBytesPerPoint : kLkTemplateBytesPerPoint);
         const bool want = fo->window_size == 10 && per_slot * c->slots.size() <= ((size_t)4 << 30) && !getenv("PC_NO_LK_TEMPLATES");
         for (auto& s : c->slots) {
             if (want && s.tmpl && s.tmpl_levels >= tl) continue;
@@ -836,7 +841,9 @@ static int enqueue_lk(pc_ctx* c, Stage& st, FrameSlot* f) {
     // source templates of this frame's keypoints (once per frame; its eight pairs load them)
     if (f->tmpl && lkp.win == 10 && lkp.max_level + 1 <= f->tmpl_levels) {
         span_begin(c, KF_LK_TMPL, lks);
-        launch_lk10_templates(view_of(*f), f->kps, f->n_kps, c->lim.max_features, lkp, f->tmpl, f->tmpl_sums, lks);
+        if (c->lk_queue_mode) launch_lk10q_templates(view_of(*f), f->kps, f->n_kps, c->lim.max_features, lkp, f->tmpl, lks);
+        else launch_lk10_templates(view_of(*f), f->kps, f->n_kps, c->lim.max_features, lkp, f->tmpl, f->tmpl_sums, lks);
+        f->tmpl_queue_layout = c->lk_queue_mode;
         span_end(c, lks);
         rc = check_launch(c, "lk templates", 1);
         if (rc) return rc;
@@ -866,6 +873,15 @@ static int enqueue_lk(pc_ctx* c, Stage& st, FrameSlot* f) {
     }
     batch.num_pairs = np;
     st.num_pairs = np;
+    // work-queue kernel: every pair of the batch brings queue-layout templates (indexed with stride max_features)
+    if (c->lk_queue_mode && lkp.win == 10 && np > 0 && batch.cap <= c->lim.max_features) {
+        bool all = true;
+        for (int k = 0; k < np; k++) {
+            const FrameSlot* src = find_slot(c, st.from[k]);
+            all = all && src->has_tmpl && src->tmpl_queue_layout && batch.pair[k].tmpl.words != nullptr;
+        }
+        if (all) { batch.queue = c->lk_queue; batch.queue_budget = c->lk_queue_budget; }
+    }
     if (np > 0) {
         const LKParams& p = lkp;
         span_begin(c, KF_LK, lks);
@@ -874,7 +890,7 @@ static int enqueue_lk(pc_ctx* c, Stage& st, FrameSlot* f) {
         span_begin(c, KF_COMPACT, lks);
         launch_lk_compact(batch, lks);
         span_end(c, lks);
-        rc = check_launch(c, "lk batch", 2);
+        rc = check_launch(c, "lk batch", batch.queue ? 3 : 2);
         if (rc) return rc;
     }
     PC_CUDA(c, cudaEventRecord(st.computed, lks));

@@ -33,6 +33,7 @@ struct FrameSlot {
     float* tmpl_sums = nullptr;
     int tmpl_levels = 0;          // levels the allocation holds
     bool has_tmpl = false;        // computed for the frame and keypoints the slot holds now
+    bool tmpl_queue_layout = false;   // which kernel wrote them (lk10q.cu's layout or lk10.cu's)
 };
 
 enum KernelFamily { KF_GRAY_PYR = 0, KF_MIN_EIG, KF_SELECT, KF_LK, KF_COMPACT, KF_RAYCAST, KF_PNP, KF_BA, KF_LK_TMPL, KF_COUNT };
@@ -131,6 +132,11 @@ struct pc_ctx {
 
     // LK dense scratch: [8][cap]
     float* lk_next = nullptr; uint8_t* lk_status = nullptr; float* lk_err = nullptr;
+    // 10x10 LK as a work queue (lk10q.cu): the launch's item counter; PC_LK_QUEUE=0 keeps the lock-step kernel,
+    // PC_LK_BUDGET=n makes a block leave after n items (0: stay until the queue is empty)
+    int* lk_queue = nullptr;
+    bool lk_queue_mode = true;
+    int lk_queue_budget = 0;
     pc::PairOut sync_out;           // outputs of the synchronous pc_lk_pair
     uint8_t* rgb_scratch = nullptr; size_t rgb_scratch_bytes = 0;   // synchronous uploads
 

@@ -90,11 +90,14 @@ struct LKParams {
 // (lk10.cu): per (level, keypoint) the five lanes' 20 pixels of Ival / Ix / Iy packed in 32 words per
 // lane, and A11, A12, A22.  words == nullptr: the LK kernel computes the templates itself.
 struct LKTemplates {
-    const uint4* words;          // [level][cap][5 lanes][8 uint4]
-    const float* sums;           // [level][cap][4]
+    const uint4* words;          // [level][cap][5 lanes][8 uint4]; queue layout: [level][cap][16 quads][5 lanes]
+    const float* sums;           // [level][cap][4] (nullptr in the queue layout: the sums live in quad 15)
     int cap;
 };
 constexpr size_t kLkTemplateBytesPerPoint = 5 * 8 * 16;     // per level
+// queue layout (lk10q.cu): Ival / Ix / Iy unpacked (15 quads per lane) + one quad of sums
+constexpr int kLkQueueQuadsPerLane = 16;
+constexpr size_t kLkQueueTemplateBytesPerPoint = (size_t)kLkQueueQuadsPerLane * 5 * 16;
 struct LKPair {
     PyramidView a, b;            // source / target frame
     LKTemplates tmpl;
@@ -111,12 +114,20 @@ struct LKBatch {
     LKPair pair[kMaxPairsPerLaunch];
     int num_pairs;
     int cap;                     // max points per pair
+    // lk10q.cu: non-null = every pair brings queue-layout templates and the launch runs as a work queue
+    // over this device counter (the launcher zeroes it); queue_budget > 0 = items a block takes before it
+    // leaves (0: blocks stay until the queue is empty)
+    int* queue;
+    int queue_budget;
 };
 void launch_lk(const LKBatch& batch, const LKParams& p, cudaStream_t s);
 void launch_lk_compact(const LKBatch& batch, cudaStream_t s);
 // Templates of frame `a`'s keypoints for every level the 10x10 kernel will visit (win must be 10).
 void launch_lk10_templates(const PyramidView& a, const float* pts, const int* n_pts, int cap, const LKParams& p,
                            uint4* words, float* sums, cudaStream_t s);
+// The same in the queue layout (kLkQueueTemplateBytesPerPoint per level and point).
+void launch_lk10q_templates(const PyramidView& a, const float* pts, const int* n_pts, int cap, const LKParams& p,
+                            uint4* words, cudaStream_t s);
 
 // ---- synthetic frame warp (synth.cu) ------------------------------------------------
 void launch_synth_warp(const uint8_t* tex, int w, int h, int tex_pitch, const double Hinv[9],

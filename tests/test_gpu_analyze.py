@@ -280,3 +280,60 @@ def test_streaming_with_preset_keypoints_on_the_borders(ctx_small):
         assert np.array_equal(idx, np.nonzero(ok)[0].astype(np.uint32)), (a, b)
         assert np.array_equal(_u32(tgt), _u32(wn[ok])), (a, b)
         assert np.array_equal(_u32(err), _u32(we[ok])), (a, b)
+
+
+def _stream_rows(ctx, w, h, frames, max_corners):
+    from polychase_b200 import capi
+    F = len(frames)
+    ctx.analyze_begin(w, h, 0, F, capi.default_gftt(max_corners=max_corners))
+    kps, pairs = {}, {}
+
+    def take(r):
+        kps[r["frame_id"]] = np.array(r["keypoints"]).copy()
+        for (a, b, rows, idx, tgt, err) in r["pairs"]:
+            pairs[(a, b)] = (np.array(idx).copy(), np.array(tgt).copy(), np.array(err).copy())
+
+    for k in range(F):
+        ctx.analyze_push(k, frames[k])
+        if ctx.analyze_pending() >= 4:
+            take(ctx.analyze_pop())
+    while ctx.analyze_pending():
+        take(ctx.analyze_pop())
+    ctx.analyze_end()
+    return kps, pairs
+
+
+@pytest.mark.parametrize("env", [{"PC_LK_QUEUE": "0"}, {"PC_LK_QUEUE": "1", "PC_LK_BUDGET": "24"},
+                                 {"PC_LK_QUEUE": "1", "PC_LK_BUDGET": "100"}])
+def test_lk_work_queue_schedules_agree(ctx_small, env, monkeypatch):
+    """The 10x10 LK runs as a work queue (lk10q.cu: a pentad takes the next (pair, keypoint) as soon as it is
+    done) -- a change of schedule only.  Every schedule (lock-step kernel, queue with blocks that leave after 24
+    or 100 items, queue with resident blocks = the session context) must give the same rows, bit for bit; one
+    pair is also compared with the oracle."""
+    from polychase_b200 import capi
+    w, h, F = 640, 480, 11
+    clip = synth.Clip(w, h, F, seed=77, first_frame=0)
+    frames = [clip.rgb(k) for k in range(F)]
+    kps0, pairs0 = _stream_rows(ctx_small, w, h, frames, 1500)
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    other = capi.Context(max_width=w, max_height=h, max_features=2048)
+    try:
+        kps1, pairs1 = _stream_rows(other, w, h, frames, 1500)
+    finally:
+        other.close()
+    assert sorted(pairs0) == sorted(pairs1) and len(pairs0) == 8 * F - 30
+    for k in range(F):
+        assert np.array_equal(kps0[k], kps1[k])
+    for key in pairs0:
+        for x, y in zip(pairs0[key], pairs1[key]):
+            assert np.array_equal(_u32(x), _u32(y)), key
+    a, b = 10, 2
+    pyr_a = restate.pyramid(restate.rgb2gray(frames[a]), 3)
+    pyr_b = restate.pyramid(restate.rgb2gray(frames[b]), 3)
+    wn, ws, we = restate.lk(pyr_a, pyr_b, kps0[a])
+    ok = ws == 1
+    idx, tgt, err = pairs0[(a, b)]
+    assert np.array_equal(idx, np.nonzero(ok)[0].astype(np.uint32))
+    assert np.array_equal(_u32(tgt), _u32(wn[ok]))
+    assert np.array_equal(_u32(err), _u32(we[ok]))
