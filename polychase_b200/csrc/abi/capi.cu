@@ -160,27 +160,76 @@ static int build_pyramid(pc_ctx* c, FrameSlot* f, const uint8_t* img_dev, size_t
     return check_launch(c, "gray+pyramid", n_launch + 1);
 }
 
-static int run_detector(pc_ctx* c, FrameSlot* f, const pc_gftt_opts* go, cudaStream_t s) {
+// One set of detector scratch for frames up to W x H (a detector stream owns one set).
+static int alloc_det_scratch(int W, int H, DetScratch& d) {
+    d.eig_pitch = (W + 31) / 32 * 32;
+    PC_CUDA(nullptr, cudaMalloc(&d.eig, sizeof(float) * (size_t)d.eig_pitch * H));
+    d.state_pitch = (W + 127) / 128 * 128;
+    PC_CUDA(nullptr, cudaMalloc(&d.state, (size_t)d.state_pitch * H));
+    PC_CUDA(nullptr, cudaMalloc(&d.cell_max, sizeof(int) * 1024));
+    // 3x3 NMS leaves at most one candidate per 2x2 block except on plateaus; w*h/4 is ample
+    d.cand_cap = std::max(1024, (int)(((size_t)W * H) / 4));
+    PC_CUDA(nullptr, cudaMalloc(&d.cand, sizeof(unsigned long long) * d.cand_cap));
+    // one block holds every detector counter that must be zero at the start of a frame, so the init
+    // launch of the min-eig stage clears them all: [0] candidate count, [8..15] select scratch,
+    // then the greedy round counters, the two 4096-bin value histograms and the short list's bin cursors
+    d.det_zero_ints = 16 + 3 * kMaxGreedyRounds + 3 * 4096;
+    PC_CUDA(nullptr, cudaMalloc(&d.det_zero, sizeof(int) * d.det_zero_ints));
+    PC_CUDA(nullptr, cudaMemset(d.det_zero, 0, sizeof(int) * d.det_zero_ints));
+    d.cand_count = d.det_zero;
+    d.sel.cap = d.cand_cap;
+    PC_CUDA(nullptr, cudaMalloc(&d.sel.accepted, sizeof(unsigned long long) * d.cand_cap));
+    d.sel.sorted_cap = 1;
+    while (d.sel.sorted_cap < d.cand_cap) d.sel.sorted_cap <<= 1;
+    PC_CUDA(nullptr, cudaMalloc(&d.sel.sorted, sizeof(unsigned long long) * d.sel.sorted_cap));
+    d.sel.sel = d.det_zero + 8;
+    d.sel.round_counters = d.det_zero + 16;
+    d.sel.hist = d.sel.round_counters + 3 * kMaxGreedyRounds;
+    d.sel.kept_hist = d.sel.hist + 4096;
+    d.sel.bin_cursor = d.sel.kept_hist + 4096;
+    PC_CUDA(nullptr, cudaMalloc(&d.sel.bin_start, sizeof(int) * 4096));
+    PC_CUDA(nullptr, cudaMalloc(&d.sel.strong, sizeof(unsigned long long) * d.cand_cap));
+    d.sel.cub_temp_bytes = select_cub_temp_bytes(d.cand_cap);
+    PC_CUDA(nullptr, cudaMalloc(&d.sel.cub_temp, d.sel.cub_temp_bytes));
+    return PC_OK;
+}
+
+static void free_det_scratch(DetScratch& d) {
+    cudaFree(d.eig); cudaFree(d.state); cudaFree(d.cell_max); cudaFree(d.cand); cudaFree(d.det_zero);
+    cudaFree(d.sel.accepted); cudaFree(d.sel.sorted); cudaFree(d.sel.cub_temp); cudaFree(d.sel.strong); cudaFree(d.sel.bin_start);
+    d = DetScratch{};
+}
+
+static DetScratch primary_scratch(const pc_ctx* c) {
+    DetScratch d;
+    d.eig = c->eig; d.eig_pitch = c->eig_pitch; d.state = c->state; d.state_pitch = c->state_pitch;
+    d.cell_max = c->cell_max; d.cand = c->cand; d.cand_cap = c->cand_cap; d.cand_count = c->cand_count;
+    d.det_zero = c->det_zero; d.det_zero_ints = c->det_zero_ints; d.sel = c->sel;
+    return d;
+}
+
+static int run_detector(pc_ctx* c, FrameSlot* f, const pc_gftt_opts* go, cudaStream_t s, const DetScratch* scratch = nullptr) {
+    const DetScratch d = scratch ? *scratch : primary_scratch(c);
     DetectGrid g;
     g.grid_rows = std::max(1, go->grid_rows);
     g.grid_cols = std::max(1, go->grid_cols);
     g.block_h = (f->h + g.grid_rows - 1) / g.grid_rows;   // gftt.cc:42-43
     g.block_w = (f->w + g.grid_cols - 1) / g.grid_cols;
     span_begin(c, KF_MIN_EIG, s);
-    launch_min_eig(f->level[0], c->eig, c->eig_pitch, g, c->cell_max, c->det_zero, c->det_zero_ints, f->n_kps, s);
+    launch_min_eig(f->level[0], d.eig, d.eig_pitch, g, d.cell_max, d.det_zero, d.det_zero_ints, f->n_kps, s);
     span_end(c, s);
     span_begin(c, KF_SELECT, s);
-    launch_nms_candidates(c->eig, c->eig_pitch, f->w, f->h, g, c->cell_max, go->quality_level, c->state,
-                          c->state_pitch, c->cand, c->cand_cap, c->cand_count, c->sel.hist, s);
-    SelectWorkspace ws = c->sel;
+    launch_nms_candidates(d.eig, d.eig_pitch, f->w, f->h, g, d.cell_max, go->quality_level, d.state,
+                          d.state_pitch, d.cand, d.cand_cap, d.cand_count, d.sel.hist, s);
+    SelectWorkspace ws = d.sel;
     ws.accepted_count = f->n_accepted;
     ws.remaining = f->greedy_remaining;
-    launch_select(c->cand, c->cand_count, c->cand_cap, c->eig, c->eig_pitch, c->state, c->state_pitch, f->w, f->h,
+    launch_select(d.cand, d.cand_count, d.cand_cap, d.eig, d.eig_pitch, d.state, d.state_pitch, f->w, f->h,
                   go->min_distance, go->max_corners, ws, f->kps, c->lim.max_features, f->n_kps, c->sm_count, s);
     span_end(c, s);
     // the candidate count lives in the shared detector scratch, which the next frame's detector clears: keep
     // this frame's value with its other counters so that an overflow is still seen when the frame is popped
-    PC_CUDA(c, cudaMemcpyAsync(f->n_kps + 3, c->cand_count, sizeof(int), cudaMemcpyDeviceToDevice, s));
+    PC_CUDA(c, cudaMemcpyAsync(f->n_kps + 3, d.cand_count, sizeof(int), cudaMemcpyDeviceToDevice, s));
     f->has_kps = true;
     f->n_kps_host = -1;
     return check_launch(c, "detector", 6);
@@ -282,7 +331,9 @@ pc_ctx::~pc_ctx() {
     if (d2h) cudaStreamSynchronize(d2h);
     if (d2h_rows) cudaStreamSynchronize(d2h_rows);
     if (side) cudaStreamSynchronize(side);
+    if (compute2) cudaStreamSynchronize(compute2);
     if (track && track->stream) cudaStreamSynchronize(track->stream);
+    if (det2) { free_det_scratch(*det2); delete det2; }
     for (auto& s : slots) {
         cudaFree(s.tmpl);
         cudaFree(s.tmpl_sums);
@@ -318,6 +369,8 @@ pc_ctx::~pc_ctx() {
     if (ba) free_ba(ba);
     if (comm) free_comm(comm);
     if (side) cudaStreamDestroy(side);
+    if (compute2) cudaStreamDestroy(compute2);
+    if (join_d) cudaEventDestroy(join_d);
     if (compute) cudaStreamDestroy(compute);
     if (h2d) cudaStreamDestroy(h2d);
     for (int k = 0; k < 3; k++) {
@@ -395,6 +448,11 @@ int pc_create(const pc_limits* limits, pc_ctx** out) {
         PC_CUDA(nullptr, cudaStreamCreateWithPriority(&cp->compute, cudaStreamNonBlocking, hi < lo ? hi + 1 : lo));
         const char* e = getenv("PC_LK_STREAM");     // PC_LK_STREAM=0: everything on the compute stream
         if (!e || atoi(e) != 0) PC_CUDA(nullptr, cudaStreamCreateWithPriority(&cp->side, cudaStreamNonBlocking, lo));
+        const char* d = getenv("PC_DET_STREAMS");   // PC_DET_STREAMS=1: one detector stream
+        if (cp->side && (!d || atoi(d) >= 2)) {
+            PC_CUDA(nullptr, cudaStreamCreateWithPriority(&cp->compute2, cudaStreamNonBlocking, hi < lo ? hi + 1 : lo));
+            PC_CUDA(nullptr, cudaEventCreateWithFlags(&cp->join_d, cudaEventDisableTiming));
+        }
     }
     PC_CUDA(nullptr, cudaStreamCreateWithFlags(&cp->h2d, cudaStreamNonBlocking));
     PC_CUDA(nullptr, cudaEventCreateWithFlags(&cp->h2d_fork, cudaEventDisableTiming));
@@ -430,36 +488,15 @@ int pc_create(const pc_limits* limits, pc_ctx** out) {
         s.n_accepted = s.n_kps + 1;
         s.greedy_remaining = s.n_kps + 2;
     }
-    cp->eig_pitch = (W + 31) / 32 * 32;
-    PC_CUDA(nullptr, cudaMalloc(&cp->eig, sizeof(float) * (size_t)cp->eig_pitch * H));
-    cp->state_pitch = (W + 127) / 128 * 128;
-    PC_CUDA(nullptr, cudaMalloc(&cp->state, (size_t)cp->state_pitch * H));
-    cp->cell_cap = 1024;      // = NMS_MAX_CELLS (mineig.cu)
-    PC_CUDA(nullptr, cudaMalloc(&cp->cell_max, sizeof(int) * cp->cell_cap));
-    // 3x3 NMS leaves at most one candidate per 2x2 block except on plateaus; w*h/4 is ample
-    cp->cand_cap = std::max(1024, (int)(((size_t)W * H) / 4));
-    PC_CUDA(nullptr, cudaMalloc(&cp->cand, sizeof(unsigned long long) * cp->cand_cap));
-    // one block holds every detector counter that must be zero at the start of a frame, so the init
-    // launch of the min-eig stage clears them all: [0] candidate count, [8..15] select scratch,
-    // then the greedy round counters, the two 4096-bin value histograms and the short list's bin cursors
-    cp->det_zero_ints = 16 + 3 * kMaxGreedyRounds + 3 * 4096;
-    PC_CUDA(nullptr, cudaMalloc(&cp->det_zero, sizeof(int) * cp->det_zero_ints));
-    PC_CUDA(nullptr, cudaMemset(cp->det_zero, 0, sizeof(int) * cp->det_zero_ints));
-    cp->cand_count = cp->det_zero;
-    cp->sel.cap = cp->cand_cap;
-    PC_CUDA(nullptr, cudaMalloc(&cp->sel.accepted, sizeof(unsigned long long) * cp->cand_cap));
-    cp->sel.sorted_cap = 1;
-    while (cp->sel.sorted_cap < cp->cand_cap) cp->sel.sorted_cap <<= 1;
-    PC_CUDA(nullptr, cudaMalloc(&cp->sel.sorted, sizeof(unsigned long long) * cp->sel.sorted_cap));
-    cp->sel.sel = cp->det_zero + 8;
-    cp->sel.round_counters = cp->det_zero + 16;
-    cp->sel.hist = cp->sel.round_counters + 3 * kMaxGreedyRounds;
-    cp->sel.kept_hist = cp->sel.hist + 4096;
-    cp->sel.bin_cursor = cp->sel.kept_hist + 4096;
-    PC_CUDA(nullptr, cudaMalloc(&cp->sel.bin_start, sizeof(int) * 4096));
-    PC_CUDA(nullptr, cudaMalloc(&cp->sel.strong, sizeof(unsigned long long) * cp->cand_cap));
-    cp->sel.cub_temp_bytes = select_cub_temp_bytes(cp->cand_cap);
-    PC_CUDA(nullptr, cudaMalloc(&cp->sel.cub_temp, cp->sel.cub_temp_bytes));
+    {
+        DetScratch d;
+        int rc = alloc_det_scratch(W, H, d);
+        if (rc) return rc;
+        cp->eig = d.eig; cp->eig_pitch = d.eig_pitch; cp->state = d.state; cp->state_pitch = d.state_pitch;
+        cp->cell_cap = 1024;      // = NMS_MAX_CELLS (mineig.cu)
+        cp->cell_max = d.cell_max; cp->cand = d.cand; cp->cand_cap = d.cand_cap; cp->cand_count = d.cand_count;
+        cp->det_zero = d.det_zero; cp->det_zero_ints = d.det_zero_ints; cp->sel = d.sel;
+    }
     PC_CUDA(nullptr, cudaMalloc(&cp->lk_next, sizeof(float) * 2 * (size_t)cap * 8));
     PC_CUDA(nullptr, cudaMalloc(&cp->lk_status, (size_t)cap * 8));
     PC_CUDA(nullptr, cudaMalloc(&cp->lk_err, sizeof(float) * (size_t)cap * 8));
@@ -482,6 +519,7 @@ int pc_synchronize(pc_ctx* c) {
     PC_CUDA(c, cudaStreamSynchronize(c->d2h));
     PC_CUDA(c, cudaStreamSynchronize(c->d2h_rows));
     if (c->side) PC_CUDA(c, cudaStreamSynchronize(c->side));
+    if (c->compute2) PC_CUDA(c, cudaStreamSynchronize(c->compute2));
     if (c->track && c->track->stream) PC_CUDA(c, cudaStreamSynchronize(c->track->stream));
     return PC_OK;
 }
@@ -735,6 +773,19 @@ int pc_analyze_begin(pc_ctx* c, const pc_video_info* vi, const pc_gftt_opts* go,
         }
     }
     if (c->side) PC_CUDA(c, cudaStreamSynchronize(c->side));
+    if (c->compute2) {
+        PC_CUDA(c, cudaStreamSynchronize(c->compute2));
+        if (!c->det2) {                              // the second detector stream's scratch set
+            c->det2 = new DetScratch();
+            int rc2 = alloc_det_scratch(c->lim.max_width, c->lim.max_height, *c->det2);
+            if (rc2) {                               // not enough memory: one detector stream
+                cudaGetLastError();
+                free_det_scratch(*c->det2);
+                delete c->det2;
+                c->det2 = nullptr;
+            }
+        }
+    }
     for (auto& s : c->slots) { s.used = false; s.has_tmpl = false; }
     // template cache of the 10x10 LK kernel: (max_level + 1) x max_features x 640 B per slot, kept as
     // long as it stays under 4 GB for the whole ring (the kernel computes templates itself otherwise)
@@ -805,11 +856,17 @@ int pc_mark(pc_ctx* c, int slot) {
         PC_CUDA(c, cudaEventRecord(c->join_c, c->side));
         PC_CUDA(c, cudaStreamWaitEvent(c->compute, c->join_c, 0));
     }
+    if (c->compute2) {
+        PC_CUDA(c, cudaEventRecord(c->join_d, c->compute2));
+        PC_CUDA(c, cudaStreamWaitEvent(c->compute, c->join_d, 0));
+    }
     if (c->track && c->track->stream) {
         PC_CUDA(c, cudaEventRecord(c->track->join, c->track->stream));
         PC_CUDA(c, cudaStreamWaitEvent(c->compute, c->track->join, 0));
     }
     PC_CUDA(c, cudaEventRecord(c->marks[slot], c->compute));
+    // work queued after the mark starts after it on every detector stream (a timed region opens with a mark)
+    if (c->compute2) PC_CUDA(c, cudaStreamWaitEvent(c->compute2, c->marks[slot], 0));
     return PC_OK;
 }
 
@@ -831,8 +888,9 @@ static int enqueue_lk(pc_ctx* c, Stage& st, FrameSlot* f) {
     const int32_t first = c->vinfo.first_frame;
     cudaStream_t lks = c->compute;
     if (c->side) {
-        // this frame's pyramid and keypoints (and, stream order, those of every earlier frame)
-        PC_CUDA(c, cudaEventRecord(st.detected, c->compute));
+        // this frame's pyramid and keypoints (and, stream order of the LK stream, those of every earlier frame:
+        // each earlier batch waited for its own frame's event)
+        PC_CUDA(c, cudaEventRecord(st.detected, st.det_stream ? st.det_stream : c->compute));
         PC_CUDA(c, cudaStreamWaitEvent(c->side, st.detected, 0));
         lks = c->side;
     }
@@ -930,6 +988,10 @@ int pc_analyze_push_frame(pc_ctx* c, int32_t frame_id, const uint8_t* rgb, size_
     st.num_pairs = 0;
 
     FrameSlot* f = acquire_slot(c, frame_id);
+    // detector stream of this frame: frames alternate between the two (each owns a scratch set)
+    const bool second = c->compute2 && c->det2 && (c->pushed_count & 1);
+    cudaStream_t ds = second ? c->compute2 : c->compute;
+    st.det_stream = ds;
     const uint8_t* dev = rgb;
     if (mem_kind != PC_MEM_DEVICE) {
         const size_t bytes = stride * (size_t)h;
@@ -942,8 +1004,10 @@ int pc_analyze_push_frame(pc_ctx* c, int32_t frame_id, const uint8_t* rgb, size_
         }
         // the staging buffer's previous contents must have been consumed by its gray kernel
         if (st.gray_pending) PC_CUDA(c, cudaStreamWaitEvent(c->h2d, st.gray_done, 0));
-        // PC_H2D_SPLIT=n (2..4): the frame travels as n slices on n streams, i.e. on several copy engines at once
-        static const int split = [] { const char* e = getenv("PC_H2D_SPLIT"); return e ? std::min(std::max(atoi(e), 1), 4) : 1; }();
+        // the frame travels as 4 slices on 4 streams, i.e. on several copy engines at once (PC_H2D_SPLIT=n, 1..4, overrides):
+        // one 24.9 MB copy reaches 36 GB/s on a PCIe 5 x16 box, slices on two or more streams 52 GB/s
+        // (profiles/r2_j_h2d_probe.json); e2e 14 273 -> 15 161 pairs/s (profiles/r2_k_streams_ab.json)
+        static const int split = [] { const char* e = getenv("PC_H2D_SPLIT"); return e ? std::min(std::max(atoi(e), 1), 4) : 4; }();
         if (split > 1 && mem_kind == PC_MEM_HOST_PINNED) {
             if (!c->h2d_extra[0])
                 for (int k = 0; k < 3; k++) {
@@ -967,13 +1031,13 @@ int pc_analyze_push_frame(pc_ctx* c, int32_t frame_id, const uint8_t* rgb, size_
             PC_CUDA(c, cudaMemcpyAsync(st.rgb_dev, rgb, bytes, cudaMemcpyHostToDevice, c->h2d));
         }
         PC_CUDA(c, cudaEventRecord(st.uploaded, c->h2d));
-        PC_CUDA(c, cudaStreamWaitEvent(c->compute, st.uploaded, 0));
+        PC_CUDA(c, cudaStreamWaitEvent(ds, st.uploaded, 0));
         dev = st.rgb_dev;
     }
-    int rc = build_pyramid(c, f, dev, stride, 3, w, h, &c->fopts, c->compute);
+    int rc = build_pyramid(c, f, dev, stride, 3, w, h, &c->fopts, ds);
     if (rc) return rc;
     if (mem_kind != PC_MEM_DEVICE) {
-        PC_CUDA(c, cudaEventRecord(st.gray_done, c->compute));
+        PC_CUDA(c, cudaEventRecord(st.gray_done, ds));
         st.gray_pending = true;
     }
     auto preset = c->preset_kps.find(frame_id);
@@ -982,13 +1046,13 @@ int pc_analyze_push_frame(pc_ctx* c, int32_t frame_id, const uint8_t* rgb, size_
         int hdr[4] = {n, n, 0, 0};
         if (n) memcpy(st.kps_host, preset->second.data(), sizeof(float) * 2 * n);
         memcpy(st.counts_host, hdr, sizeof(hdr));
-        if (n) PC_CUDA(c, cudaMemcpyAsync(f->kps, st.kps_host, sizeof(float) * 2 * n, cudaMemcpyHostToDevice, c->compute));
-        PC_CUDA(c, cudaMemcpyAsync(f->n_kps, st.counts_host, sizeof(hdr), cudaMemcpyHostToDevice, c->compute));
+        if (n) PC_CUDA(c, cudaMemcpyAsync(f->kps, st.kps_host, sizeof(float) * 2 * n, cudaMemcpyHostToDevice, ds));
+        PC_CUDA(c, cudaMemcpyAsync(f->n_kps, st.counts_host, sizeof(hdr), cudaMemcpyHostToDevice, ds));
         f->has_kps = true;
         f->n_kps_host = n;
         c->preset_kps.erase(preset);
     } else {
-        rc = run_detector(c, f, &c->gopts, c->compute);
+        rc = run_detector(c, f, &c->gopts, ds, second ? c->det2 : nullptr);
         if (rc) return rc;
     }
     st.is_halo = c->pushed_count < c->halo_frames;

@@ -53,6 +53,7 @@ struct PairOut {              // compacted LK rows of one pair (device) + pinned
 struct Stage {                // one in-flight frame of the streaming analyzer
     uint8_t* rgb_dev = nullptr;       // staging for host-provided frames
     size_t rgb_bytes = 0;
+    cudaStream_t det_stream = nullptr;   // the detector stream this frame's pyramid + detector were queued on
     PairOut dev[8], host[8];          // views into the two slabs below
     // One device slab and one pinned mirror per stage: [8 row counts | pair 0: idx, tgt, err | pair 1 ...],
     // so a frame's result travels in one copy (capi.cu: alloc_stage_rows).
@@ -97,6 +98,16 @@ struct TrackChain {
     size_t cap_rows = 0;
 };
 
+// One set of detector scratch (a detector stream owns one).
+struct DetScratch {
+    float* eig = nullptr; int eig_pitch = 0;
+    uint8_t* state = nullptr; int state_pitch = 0;
+    int* cell_max = nullptr;
+    unsigned long long* cand = nullptr; int cand_cap = 0; int* cand_count = nullptr;
+    int* det_zero = nullptr; int det_zero_ints = 0;
+    SelectWorkspace sel{};
+};
+
 struct MeshData;   // track.cu
 struct BAData;     // ba.cu
 struct CommData;   // comm.cu
@@ -116,6 +127,12 @@ struct pc_ctx {
     // streaming analyzer: LK batches run on this low-priority stream next to the following frame's
     // pyramid + detector on `compute` (nullptr = everything on `compute`)
     cudaStream_t side = nullptr;
+    // second detector stream (+ scratch set, allocated by the first analyze pass): frames alternate between
+    // `compute` and `compute2`, so that one frame's latency-bound selection chain (a 16-CTA cluster) overlaps the
+    // next frame's pyramid / min-eig / NMS instead of serialising the detector.  PC_DET_STREAMS=1 disables it.
+    cudaStream_t compute2 = nullptr;
+    cudaEvent_t join_d = nullptr;
+    pc::DetScratch* det2 = nullptr;
     std::string err;
     uint64_t launches = 0;
     uint64_t stamp = 0;
@@ -132,10 +149,11 @@ struct pc_ctx {
 
     // LK dense scratch: [8][cap]
     float* lk_next = nullptr; uint8_t* lk_status = nullptr; float* lk_err = nullptr;
-    // 10x10 LK as a work queue (lk10q.cu): the launch's item counter; PC_LK_QUEUE=0 keeps the lock-step kernel,
+    // 10x10 LK as a work queue (lk10q.cu), opt-in with PC_LK_QUEUE=1: measured slower than the lock-step kernel on
+    // the benchmark clip (profiles/r2_ij_lk_queue_ab.json).  lk_queue = the launch's item counter;
     // PC_LK_BUDGET=n makes a block leave after n items (0: stay until the queue is empty)
     int* lk_queue = nullptr;
-    bool lk_queue_mode = true;
+    bool lk_queue_mode = false;
     int lk_queue_budget = 0;
     pc::PairOut sync_out;           // outputs of the synchronous pc_lk_pair
     uint8_t* rgb_scratch = nullptr; size_t rgb_scratch_bytes = 0;   // synchronous uploads

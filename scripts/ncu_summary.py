@@ -60,3 +60,7 @@ tot = sum(a[0] for a in agg) or 1
 print(f"hottest source lines (of {tot} warp instructions):")
 for a in sorted(agg, reverse=True)[:top]:
     print(f"  {a[0] / tot * 100:5.1f}% inst  {a[1]:6d} samples  {a[2]}:{a[3]:<4d} {a[4]}")
+tot_s = sum(a[1] for a in agg) or 1
+print(f"source lines with the most warp samples (of {tot_s}; where warps wait):")
+for a in sorted(agg, key=lambda a: -a[1])[:top]:
+    print(f"  {a[1] / tot_s * 100:5.1f}% samples  {a[0] / tot * 100:5.1f}% inst  {a[2]}:{a[3]:<4d} {a[4]}")
