@@ -247,7 +247,7 @@ static LKParams make_lk_params(const pc_flow_opts* fo) {
 }
 
 static void fill_pair(pc_ctx* c, LKPair& p, const FrameSlot& a, const FrameSlot& b, int k, const PairOut& out,
-                      bool use_templates = false) {
+                      bool use_templates = false, bool second_set = false) {
     const int cap = c->lim.max_features;
     p.a = view_of(a);
     p.b = view_of(b);
@@ -255,9 +255,9 @@ static void fill_pair(pc_ctx* c, LKPair& p, const FrameSlot& a, const FrameSlot&
     if (use_templates && a.has_tmpl) p.tmpl = LKTemplates{a.tmpl, a.tmpl_queue_layout ? nullptr : a.tmpl_sums, cap};
     p.pts = a.kps;
     p.n_pts = a.n_kps;
-    p.next = c->lk_next + (size_t)k * cap * 2;
-    p.status = c->lk_status + (size_t)k * cap;
-    p.err = c->lk_err + (size_t)k * cap;
+    p.next = (second_set ? c->lk_next2 : c->lk_next) + (size_t)k * cap * 2;
+    p.status = (second_set ? c->lk_status2 : c->lk_status) + (size_t)k * cap;
+    p.err = (second_set ? c->lk_err2 : c->lk_err) + (size_t)k * cap;
     p.out_idx = out.idx;
     p.out_tgt = out.tgt;
     p.out_err = out.err;
@@ -332,7 +332,9 @@ pc_ctx::~pc_ctx() {
     if (d2h_rows) cudaStreamSynchronize(d2h_rows);
     if (side) cudaStreamSynchronize(side);
     if (compute2) cudaStreamSynchronize(compute2);
+    if (side2) cudaStreamSynchronize(side2);
     if (track && track->stream) cudaStreamSynchronize(track->stream);
+    cudaFree(lk_next2); cudaFree(lk_status2); cudaFree(lk_err2);
     if (det2) { free_det_scratch(*det2); delete det2; }
     for (auto& s : slots) {
         cudaFree(s.tmpl);
@@ -354,6 +356,7 @@ pc_ctx::~pc_ctx() {
         if (st.uploaded) cudaEventDestroy(st.uploaded);
         if (st.gray_done) cudaEventDestroy(st.gray_done);
         if (st.detected) cudaEventDestroy(st.detected);
+        if (st.templates) cudaEventDestroy(st.templates);
         if (st.computed) cudaEventDestroy(st.computed);
         if (st.downloaded) cudaEventDestroy(st.downloaded);
     }
@@ -371,6 +374,8 @@ pc_ctx::~pc_ctx() {
     if (side) cudaStreamDestroy(side);
     if (compute2) cudaStreamDestroy(compute2);
     if (join_d) cudaEventDestroy(join_d);
+    if (side2) cudaStreamDestroy(side2);
+    if (join_e) cudaEventDestroy(join_e);
     if (compute) cudaStreamDestroy(compute);
     if (h2d) cudaStreamDestroy(h2d);
     for (int k = 0; k < 3; k++) {
@@ -448,6 +453,11 @@ int pc_create(const pc_limits* limits, pc_ctx** out) {
         PC_CUDA(nullptr, cudaStreamCreateWithPriority(&cp->compute, cudaStreamNonBlocking, hi < lo ? hi + 1 : lo));
         const char* e = getenv("PC_LK_STREAM");     // PC_LK_STREAM=0: everything on the compute stream
         if (!e || atoi(e) != 0) PC_CUDA(nullptr, cudaStreamCreateWithPriority(&cp->side, cudaStreamNonBlocking, lo));
+        const char* l2 = getenv("PC_LK_STREAMS");   // PC_LK_STREAMS=1: one LK stream
+        if (cp->side && (!l2 || atoi(l2) >= 2)) {
+            PC_CUDA(nullptr, cudaStreamCreateWithPriority(&cp->side2, cudaStreamNonBlocking, lo));
+            PC_CUDA(nullptr, cudaEventCreateWithFlags(&cp->join_e, cudaEventDisableTiming));
+        }
         const char* d = getenv("PC_DET_STREAMS");   // PC_DET_STREAMS=1: one detector stream
         if (cp->side && (!d || atoi(d) >= 2)) {
             PC_CUDA(nullptr, cudaStreamCreateWithPriority(&cp->compute2, cudaStreamNonBlocking, hi < lo ? hi + 1 : lo));
@@ -520,6 +530,7 @@ int pc_synchronize(pc_ctx* c) {
     PC_CUDA(c, cudaStreamSynchronize(c->d2h_rows));
     if (c->side) PC_CUDA(c, cudaStreamSynchronize(c->side));
     if (c->compute2) PC_CUDA(c, cudaStreamSynchronize(c->compute2));
+    if (c->side2) PC_CUDA(c, cudaStreamSynchronize(c->side2));
     if (c->track && c->track->stream) PC_CUDA(c, cudaStreamSynchronize(c->track->stream));
     return PC_OK;
 }
@@ -768,11 +779,25 @@ int pc_analyze_begin(pc_ctx* c, const pc_video_info* vi, const pc_gftt_opts* go,
             PC_CUDA(c, cudaEventCreateWithFlags(&st.uploaded, cudaEventDisableTiming));
             PC_CUDA(c, cudaEventCreateWithFlags(&st.gray_done, cudaEventDisableTiming));
             PC_CUDA(c, cudaEventCreateWithFlags(&st.detected, cudaEventDisableTiming));
+            PC_CUDA(c, cudaEventCreateWithFlags(&st.templates, cudaEventDisableTiming));
             PC_CUDA(c, cudaEventCreateWithFlags(&st.computed, cudaEventDisableTiming));
             PC_CUDA(c, cudaEventCreateWithFlags(&st.downloaded, cudaEventDisableTiming));
         }
     }
     if (c->side) PC_CUDA(c, cudaStreamSynchronize(c->side));
+    if (c->side2) {
+        PC_CUDA(c, cudaStreamSynchronize(c->side2));
+        if (!c->lk_next2) {                          // the second LK stream's dense scratch
+            const size_t cap = (size_t)c->lim.max_features;
+            if (cudaMalloc(&c->lk_next2, sizeof(float) * 2 * cap * 8) != cudaSuccess ||
+                cudaMalloc(&c->lk_status2, cap * 8) != cudaSuccess ||
+                cudaMalloc(&c->lk_err2, sizeof(float) * cap * 8) != cudaSuccess) {
+                cudaGetLastError();
+                cudaFree(c->lk_next2); cudaFree(c->lk_status2); cudaFree(c->lk_err2);
+                c->lk_next2 = nullptr; c->lk_status2 = nullptr; c->lk_err2 = nullptr;
+            }
+        }
+    }
     if (c->compute2) {
         PC_CUDA(c, cudaStreamSynchronize(c->compute2));
         if (!c->det2) {                              // the second detector stream's scratch set
@@ -860,6 +885,10 @@ int pc_mark(pc_ctx* c, int slot) {
         PC_CUDA(c, cudaEventRecord(c->join_d, c->compute2));
         PC_CUDA(c, cudaStreamWaitEvent(c->compute, c->join_d, 0));
     }
+    if (c->side2) {
+        PC_CUDA(c, cudaEventRecord(c->join_e, c->side2));
+        PC_CUDA(c, cudaStreamWaitEvent(c->compute, c->join_e, 0));
+    }
     if (c->track && c->track->stream) {
         PC_CUDA(c, cudaEventRecord(c->track->join, c->track->stream));
         PC_CUDA(c, cudaStreamWaitEvent(c->compute, c->track->join, 0));
@@ -887,13 +916,25 @@ static int enqueue_lk(pc_ctx* c, Stage& st, FrameSlot* f) {
     const int32_t frame_id = st.frame_id;
     const int32_t first = c->vinfo.first_frame;
     cudaStream_t lks = c->compute;
+    // batches alternate between the two LK streams (each has its dense scratch set)
+    const bool second_lk = c->side2 && c->lk_next2 && (frame_id & 1);
     if (c->side) {
-        // this frame's pyramid and keypoints (and, stream order of the LK stream, those of every earlier frame:
-        // each earlier batch waited for its own frame's event)
+        lks = second_lk ? c->side2 : c->side;
+        // this frame's pyramid and keypoints
         PC_CUDA(c, cudaEventRecord(st.detected, st.det_stream ? st.det_stream : c->compute));
-        PC_CUDA(c, cudaStreamWaitEvent(c->side, st.detected, 0));
-        lks = c->side;
+        PC_CUDA(c, cudaStreamWaitEvent(lks, st.detected, 0));
+        // ... and those of the earlier frames: frames j-2, j-4, j-8 by the order of this LK stream (their batches ran
+        // on it and waited for their own events); frame j-1's pyramid, keypoints and templates were produced for / by
+        // the batch on the other LK stream
+        if (c->side2 && c->lk_next2) {
+            for (auto& other : c->stages)
+                if (&other != &st && other.busy && other.frame_id == frame_id - 1) {
+                    PC_CUDA(c, cudaStreamWaitEvent(lks, other.detected, 0));
+                    if (other.templates_recorded) PC_CUDA(c, cudaStreamWaitEvent(lks, other.templates, 0));
+                }
+        }
     }
+    st.templates_recorded = false;
     const LKParams lkp = make_lk_params(&c->fopts);
     int rc;
     // source templates of this frame's keypoints (once per frame; its eight pairs load them)
@@ -906,6 +947,10 @@ static int enqueue_lk(pc_ctx* c, Stage& st, FrameSlot* f) {
         rc = check_launch(c, "lk templates", 1);
         if (rc) return rc;
         f->has_tmpl = true;
+        if (c->side) {
+            PC_CUDA(c, cudaEventRecord(st.templates, lks));
+            st.templates_recorded = true;
+        }
     }
     LKBatch batch{};
     batch.cap = c->lim.max_features;
@@ -918,10 +963,10 @@ static int enqueue_lk(pc_ctx* c, Stage& st, FrameSlot* f) {
         FrameSlot* o = find_slot(c, other);
         if (!o) return fail(c, PC_ERR_STATE, "frame " + std::to_string(other) + " fell out of the ring");
         st.from[np] = other; st.to[np] = frame_id;
-        fill_pair(c, batch.pair[np], *o, *f, np, st.dev[np], true);
+        fill_pair(c, batch.pair[np], *o, *f, np, st.dev[np], true, second_lk);
         np++;
         st.from[np] = frame_id; st.to[np] = other;
-        fill_pair(c, batch.pair[np], *f, *o, np, st.dev[np], true);
+        fill_pair(c, batch.pair[np], *f, *o, np, st.dev[np], true, second_lk);
         np++;
     }
     // presets may exceed max_corners
@@ -938,7 +983,7 @@ static int enqueue_lk(pc_ctx* c, Stage& st, FrameSlot* f) {
             const FrameSlot* src = find_slot(c, st.from[k]);
             all = all && src->has_tmpl && src->tmpl_queue_layout && batch.pair[k].tmpl.words != nullptr;
         }
-        if (all) { batch.queue = c->lk_queue; batch.queue_budget = c->lk_queue_budget; }
+        if (all) { batch.queue = c->lk_queue + (second_lk ? 1 : 0); batch.queue_budget = c->lk_queue_budget; }
     }
     if (np > 0) {
         const LKParams& p = lkp;

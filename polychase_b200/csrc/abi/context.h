@@ -54,6 +54,8 @@ struct Stage {                // one in-flight frame of the streaming analyzer
     uint8_t* rgb_dev = nullptr;       // staging for host-provided frames
     size_t rgb_bytes = 0;
     cudaStream_t det_stream = nullptr;   // the detector stream this frame's pyramid + detector were queued on
+    cudaEvent_t templates = nullptr;     // this frame's LK source templates are written (recorded on its LK stream)
+    bool templates_recorded = false;
     PairOut dev[8], host[8];          // views into the two slabs below
     // One device slab and one pinned mirror per stage: [8 row counts | pair 0: idx, tgt, err | pair 1 ...],
     // so a frame's result travels in one copy (capi.cu: alloc_stage_rows).
@@ -132,6 +134,11 @@ struct pc_ctx {
     // next frame's pyramid / min-eig / NMS instead of serialising the detector.  PC_DET_STREAMS=1 disables it.
     cudaStream_t compute2 = nullptr;
     cudaEvent_t join_d = nullptr;
+    // second LK stream (+ dense scratch set): the batches of consecutive frames alternate between `side` and `side2`,
+    // so one batch's tail wave, template launch and compaction overlap the next batch.  PC_LK_STREAMS=1 disables it.
+    cudaStream_t side2 = nullptr;
+    cudaEvent_t join_e = nullptr;
+    float* lk_next2 = nullptr; uint8_t* lk_status2 = nullptr; float* lk_err2 = nullptr;
     pc::DetScratch* det2 = nullptr;
     std::string err;
     uint64_t launches = 0;
