@@ -597,6 +597,16 @@ def main():
     # every other family fills the chip while it runs
     sm_share = {"pnp": 16.0 / 148.0}
     dominant = max(fam, key=lambda k: fam[k][0] * sm_share.get(k, 1.0))
+    # With several detector / LK streams the event spans of the families overlap and include the wait for SM slots, so
+    # the family that needs the most SM-time is taken from the committed launch list of this configuration
+    # (profiles/roofline_traffic.json: isolated duration x share of the SMs the kernel holds) when there is one.
+    try:
+        prof_dom = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get("%s/%s" % (args.config, args.motion), {})
+        cand = {k: v.get("sm_us", 0.0) for k, v in prof_dom.items() if k in fam and fam[k][1]}
+        if cand:
+            dominant = max(cand, key=cand.get)
+    except Exception:
+        pass
     step_ms = sum(v[0] for v in fam.values())
     n_out = res["rows"] / max(res["pairs"], 1)
     per_launch = {
