@@ -9,6 +9,13 @@
 
 #include "context.h"
 
+#include <ctype.h>
+#include <stdio.h>
+#ifdef __linux__
+#include <sys/syscall.h>
+#include <unistd.h>
+#endif
+
 namespace pc {
 
 static std::mutex g_err_mtx;
@@ -1218,12 +1225,43 @@ int pc_device_free(pc_ctx* c, void* p) {
     PC_CUDA(c, cudaFree(p));
     return PC_OK;
 }
+// NUMA node the device hangs off (/sys/bus/pci/devices/<bus id>/numa_node), -1 when unknown.
+static int device_numa_node(int device) {
+    char id[32] = {0};
+    if (cudaDeviceGetPCIBusId(id, sizeof(id), device) != cudaSuccess) { cudaGetLastError(); return -1; }
+    for (char* p = id; *p; p++) *p = (char)tolower(*p);
+    const std::string path = std::string("/sys/bus/pci/devices/") + id + "/numa_node";
+    FILE* f = fopen(path.c_str(), "r");
+    if (!f) return -1;
+    int node = -1;
+    if (fscanf(f, "%d", &node) != 1) node = -1;
+    fclose(f);
+    return node;
+}
+
 int pc_host_alloc_pinned(pc_ctx* c, size_t bytes, void** out) {
     PC_CUDA(c, cudaSetDevice(c->device));
+    // The pages of an upload ring should live on the NUMA node the GPU hangs off: with eight ranks on one box every
+    // upload otherwise crosses the socket interconnect from whichever node the processes happened to start on
+    // (profiles/r2_n_h2d_numa_probe.json).  Preferred, not bound: the allocation still succeeds when that node is
+    // full or outside the cpuset.  PC_PINNED_NUMA=0 leaves the process policy alone.
+    static const bool numa = getenv("PC_PINNED_NUMA") == nullptr || atoi(getenv("PC_PINNED_NUMA")) != 0;
+    const int node = numa ? device_numa_node(c->device) : -1;
+    bool policy_set = false;
+#ifdef __linux__
+    if (node >= 0 && node < 64) {
+        unsigned long mask = 1ul << node;
+        policy_set = syscall(SYS_set_mempolicy, 1 /* MPOL_PREFERRED */, &mask, 64ul) == 0;
+    }
+#endif
     // PC_PINNED_WC=1: write-combined page-locked memory (frames are written once by the host and only read by the
     // copy engine; write-combined pages are not snooped during the transfer)
     static const bool wc = getenv("PC_PINNED_WC") != nullptr && atoi(getenv("PC_PINNED_WC")) != 0;
-    PC_CUDA(c, cudaHostAlloc(out, bytes, wc ? cudaHostAllocWriteCombined : cudaHostAllocDefault));
+    const cudaError_t e = cudaHostAlloc(out, bytes, wc ? cudaHostAllocWriteCombined : cudaHostAllocDefault);
+#ifdef __linux__
+    if (policy_set) syscall(SYS_set_mempolicy, 0 /* MPOL_DEFAULT */, nullptr, 0ul);
+#endif
+    PC_CUDA(c, e);
     return PC_OK;
 }
 int pc_host_free_pinned(pc_ctx* c, void* p) {
