@@ -291,6 +291,8 @@ def main():
     ap.add_argument("--plugin-frames", type=int, default=256)
     ap.add_argument("--plugin-only", action="store_true", help="run only the OpticalFlowThread block (used by the main run)")
     ap.add_argument("--depth", type=int, default=16, help="frames in flight in the streaming analyzer")
+    ap.add_argument("--equal-shards", action="store_true",
+                    help="N > 1, e2e leg: 32 frames per rank and step instead of shares proportional to the upload rates")
     ap.add_argument("--diag", action="store_true",
                     help="also time upload-only and download-only legs and the raw H2D copy rate (stderr)")
     args = ap.parse_args()
@@ -444,7 +446,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def one_pass(n_steps: int, mem_kind: int, base_ptr: int, ring: int, download: bool, sweep, timed: bool):
+    def one_pass(n_steps: int, mem_kind: int, base_ptr: int, ring: int, download: bool, sweep, timed: bool, fps: int = fps):
         """One Analyze(+Track) pass over this rank's sub-sequence: the halo, then n_steps * fps own frames."""
         ctx.analyze_begin(w, h, start - halo, 10 ** 6, gftt, flow)
         ctx.analyze_set_halo(halo)
@@ -472,9 +474,9 @@ def main():
             take()
         return pairs, rows
 
-    def timed_leg(mem_kind: int, base_ptr: int, ring: int, download: bool):
+    def timed_leg(mem_kind: int, base_ptr: int, ring: int, download: bool, fps: int = fps):
         sweep = Sweep(ring) if track else None
-        one_pass(args.warmup, mem_kind, base_ptr, ring, download, sweep, False)      # W untimed warm-up steps
+        one_pass(args.warmup, mem_kind, base_ptr, ring, download, sweep, False, fps)      # W untimed warm-up steps
         ctx.analyze_end()
         ctx.timing_read(reset=True)
         ctx.timing_enable(True)
@@ -484,7 +486,7 @@ def main():
         sampler.start()
         ctx.mark(0)
         t0 = time.perf_counter()
-        pairs, rows = one_pass(args.steps, mem_kind, base_ptr, ring, download, sweep, True)   # K steps (+ the halo)
+        pairs, rows = one_pass(args.steps, mem_kind, base_ptr, ring, download, sweep, True, fps)   # K steps (+ the halo)
         ctx.mark(1)                                          # recorded after all the work
         ctx.synchronize()
         barrier()
@@ -519,7 +521,6 @@ def main():
         for i in range(ring):                                # fill the pinned ring from the device clip
             ctx.lib.pc_memcpy_d2h(ctx.h, ctypes.c_void_p(host_ptr + i * frame_bytes),
                                   ctypes.c_void_p(dev_frames + i * frame_bytes), frame_bytes)
-        e2e_res = timed_leg(capi.PC_MEM_HOST_PINNED, host_ptr, ring, download=True)
         # this rank's raw pinned host->device copy rate, all ranks copying at once (what bounds e2e)
         src = torch.empty(frame_bytes, dtype=torch.uint8).pin_memory()
         dst = torch.empty(frame_bytes, dtype=torch.uint8, device="cuda")
@@ -533,6 +534,21 @@ def main():
         torch.cuda.synchronize()
         h2d_gbs = 20 * frame_bytes / (ev[0].elapsed_time(ev[1]) * 1e-3) / 1e9
         del src, dst
+        # Ingest-proportional shards (N > 1): the GPUs of one box do not see the same host link -- with eight ranks
+        # uploading, four B200s of the pool's boxes receive 23-25 GB/s and four 35-39 GB/s (profiles/r2_n_h2d_numa_probe.json)
+        # -- and with equal shards the slow ranks set the pace.  Every rank takes a share of the step's
+        # world * frames_per_step frames proportional to the upload rate it has just measured, so all ranks finish
+        # together; the work of the whole job per step is unchanged.  --equal-shards keeps 32 frames per rank.
+        e2e_fps = fps
+        e2e_fps_all = [fps] * world
+        if world > 1 and not args.equal_shards:
+            rates = torch.zeros(world, dtype=torch.float64, device="cuda")
+            rates[rank] = h2d_gbs
+            dist.all_reduce(rates)
+            share = (rates / rates.sum()).cpu().numpy()
+            e2e_fps_all = [max(8, int(round(fps * world * float(x)))) for x in share]
+            e2e_fps = e2e_fps_all[rank]
+        e2e_res = timed_leg(capi.PC_MEM_HOST_PINNED, host_ptr, ring, download=True, fps=e2e_fps)
         if args.diag and rank == 0:
             up = timed_leg(capi.PC_MEM_HOST_PINNED, host_ptr, ring, download=False)
             down = timed_leg(capi.PC_MEM_DEVICE, dev_frames, n_frames, download=True)
@@ -577,9 +593,12 @@ def main():
     if e2e is not None:
         e_s = reduce_max(e2e["dev_ms"]) * 1e-3
         e_pairs = reduce_sum(e2e["pairs"])
-        rows_per_step = e2e["rows"] / args.steps
+        rows_per_step = reduce_sum(e2e["rows"]) / world / args.steps       # per rank, averaged over the ranks
         line["e2e"] = {"value": e_pairs / e_s, "unit": "frame-pairs/s",
-                       "h2d_bytes_per_step": int(frame_bytes * fps),
+                       "h2d_bytes_per_step": int(frame_bytes * sum(e2e_fps_all) / world),
+                       "frames_per_step_per_rank": e2e_fps_all,
+                       "sharding": ("equal shards" if len(set(e2e_fps_all)) == 1 else
+                                    "shares of the step's frames proportional to each rank's measured upload rate"),
                        "d2h_bytes_per_step": int(rows_per_step * 16 + fps * max_corners * 8),
                        "wall_s": e2e["wall_s"], "clocks": e2e["clocks"],
                        "h2d_pinned_gbs_per_gpu": {"min": reduce_min(h2d_gbs), "max": reduce_max(h2d_gbs),

@@ -108,20 +108,31 @@ __global__ void __launch_bounds__(A_THREADS) gray_l1_tma_kernel(const __grid_con
         tma_load_2d(&S.rgb[0][0], &tm_rgb, (3 * ax0 - A_RGB_SKIP) / 4, ay0, &S.bar);   // x in 4-byte elements: 96 bx - 4
     }
     mbar_wait(&S.bar, 0);
-    // gray of the whole patch, four pixels (12 bytes = 3 words) per step; edge CTAs read through REFLECT_101
+    // gray of the whole patch, four pixels (12 bytes = 3 words) per step.  The 15-bit coefficients are split into
+    // bytes (9798 = 38 * 256 + 70, 19235 = 75 * 256 + 35, 3735 = 14 * 256 + 151) so that a pixel costs two DP4A on
+    // its three bytes as they lie in memory (the fourth byte meets a zero coefficient: no masking, no byte
+    // extraction) instead of three extractions and three multiplies.  Edge CTAs read the pixels that lie outside
+    // the image through REFLECT_101; everything inside takes the same fast path.
     const bool edge = ax0 < 0 || ay0 < 0 || ax0 + A_IW > w || ay0 + A_IH > h;
     constexpr int GPR = A_IW / 4;                // 34 groups per row
-    for (int idx = tid; idx < A_IH * GPR; idx += A_THREADS) {
-        const int r = idx / GPR, g = idx - r * GPR;
+    constexpr uint32_t CH = 38u | (75u << 8) | (14u << 16), CL = 70u | (35u << 8) | (151u << 16);
+    // fixed mapping (no per-step division): thread -> (row of a 7-row pass, group); 238 of the 256 threads work
+    constexpr int RPP = A_THREADS / GPR;         // 7 rows per pass, 5 passes
+    const int g = tid % GPR, r0 = tid / GPR;
+    const bool cols_in = ax0 + 4 * g >= 0 && ax0 + 4 * g + 3 < w;
+    const bool own_col = g >= 1 && g <= 2 * A_TW / 4;
+    for (int r = r0; r < A_IH && r0 < RPP; r += RPP) {
         uint32_t out;
-        if (!edge) {
+        const bool inside = !edge || (cols_in && (unsigned)(ay0 + r) < (unsigned)h);
+        if (inside) {
             const uint32_t* p = reinterpret_cast<const uint32_t*>(&S.rgb[r][A_RGB_SKIP + 12 * g]);
             const uint32_t a = p[0], b = p[1], c = p[2];
-            const uint32_t p0 = gray_of(a & 255u, (a >> 8) & 255u, (a >> 16) & 255u);
-            const uint32_t p1 = gray_of(a >> 24, b & 255u, (b >> 8) & 255u);
-            const uint32_t p2 = gray_of((b >> 16) & 255u, b >> 24, c & 255u);
-            const uint32_t p3 = gray_of((c >> 8) & 255u, (c >> 16) & 255u, c >> 24);
-            out = p0 | (p1 << 8) | (p2 << 16) | (p3 << 24);
+            const uint32_t x0 = a, x1 = __funnelshift_r(a, b, 24), x2 = __funnelshift_r(b, c, 16), x3 = c >> 8;
+            const uint32_t p0 = (__dp4a(x0, CH, 0u) * 256u + __dp4a(x0, CL, 1u << 14)) >> 15;
+            const uint32_t p1 = (__dp4a(x1, CH, 0u) * 256u + __dp4a(x1, CL, 1u << 14)) >> 15;
+            const uint32_t p2 = (__dp4a(x2, CH, 0u) * 256u + __dp4a(x2, CL, 1u << 14)) >> 15;
+            const uint32_t p3 = (__dp4a(x3, CH, 0u) * 256u + __dp4a(x3, CL, 1u << 14)) >> 15;
+            out = __byte_perm(__byte_perm(p0, p1, 0x0040), __byte_perm(p2, p3, 0x0040), 0x5410);
         } else {
             // (rows / columns further out than any output needs may map outside the patch: clamped, never used)
             const int sr = clampi(reflect101(ay0 + r, h) - ay0, 0, A_IH - 1);
@@ -134,24 +145,35 @@ __global__ void __launch_bounds__(A_THREADS) gray_l1_tma_kernel(const __grid_con
             }
         }
         *reinterpret_cast<uint32_t*>(&S.gray[r][4 * g]) = out;
-        if (r >= 2 && r < 2 + 2 * A_TH && g >= 1 && g <= 2 * A_TW / 4)
-            *reinterpret_cast<uint32_t*>(&S.out0[r - 2][4 * (g - 1)]) = out;
+        if (own_col && r >= 2 && r < 2 + 2 * A_TH) *reinterpret_cast<uint32_t*>(&S.out0[r - 2][4 * (g - 1)]) = out;
     }
     __syncthreads();
-    for (int idx = tid; idx < A_IH * A_TW; idx += A_THREADS) {
-        const int r = idx / A_TW, j = idx - r * A_TW;
-        const uint8_t* t = &S.gray[r][2 * j + 2];
-        S.hsum[r][j] = (uint16_t)(t[0] + 4 * t[1] + 6 * t[2] + 4 * t[3] + t[4]);
+    // horizontal 1-4-6-4-1 pass, two outputs per step in 16-bit fields: outputs 2q' and 2q'+1 are centred on bytes
+    // 0 and 2 of gray word q = q' + 1; E = (b0, b2), O = (b1, b3) of a word as packed 16-bit pairs
+    for (int idx = tid; idx < A_IH * (A_TW / 2); idx += A_THREADS) {
+        const int r = idx / (A_TW / 2), qp = idx - r * (A_TW / 2);
+        const uint32_t* gw = reinterpret_cast<const uint32_t*>(&S.gray[r][0]) + qp;
+        const uint32_t wm = gw[0], w0 = gw[1], wp = gw[2];
+        const uint32_t Em = wm & 0x00ff00ffu, Om = (wm >> 8) & 0x00ff00ffu;
+        const uint32_t E0 = w0 & 0x00ff00ffu, O0 = (w0 >> 8) & 0x00ff00ffu;
+        const uint32_t Ep = wp & 0x00ff00ffu;
+        const uint32_t tm2 = __funnelshift_r(Em, E0, 16);        // (b2 of q-1, b0 of q)
+        const uint32_t tm1 = __funnelshift_r(Om, O0, 16);        // (b3 of q-1, b1 of q)
+        const uint32_t tp2 = __funnelshift_r(E0, Ep, 16);        // (b2 of q, b0 of q+1)
+        const uint32_t sum = tm2 + tp2 + 4u * (tm1 + O0) + 6u * E0;   // <= 16 * 255 per field
+        *reinterpret_cast<uint32_t*>(&S.hsum[r][2 * qp]) = sum;
     }
     __syncthreads();
+    // vertical pass, the same packing (16 * 4080 + 128 < 65536): four outputs = two packed columns pairs per thread
     {
         const int i = tid / 16, j4 = (tid % 16) * 4, r = 2 * i;
         uint32_t o = 0;
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const int j = j4 + k;
-            o |= (uint32_t)((S.hsum[r][j] + 4 * S.hsum[r + 1][j] + 6 * S.hsum[r + 2][j] + 4 * S.hsum[r + 3][j] +
-                             S.hsum[r + 4][j] + 128) >> 8) << (8 * k);
+        for (int k = 0; k < 2; k++) {
+            const int j = j4 + 2 * k;
+            auto hs = [&](int rr) { return *reinterpret_cast<const uint32_t*>(&S.hsum[rr][j]); };
+            const uint32_t v = hs(r) + hs(r + 4) + 4u * (hs(r + 1) + hs(r + 3)) + 6u * hs(r + 2) + 0x00800080u;
+            o |= (((v >> 8) & 0xffu) | ((v >> 16) & 0xff00u)) << (16 * k);
         }
         *reinterpret_cast<uint32_t*>(&S.out1[i][j4]) = o;
     }
