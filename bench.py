@@ -288,7 +288,7 @@ def main():
     ap.add_argument("--no-ba", action="store_true", help="skip the configs[4] refine block")
     ap.add_argument("--no-plugin", action="store_true", help="skip the polychase_core.OpticalFlowThread block")
     ap.add_argument("--ba-frames", type=int, default=200)
-    ap.add_argument("--plugin-frames", type=int, default=256)
+    ap.add_argument("--plugin-frames", type=int, default=1000)
     ap.add_argument("--plugin-only", action="store_true", help="run only the OpticalFlowThread block (used by the main run)")
     ap.add_argument("--depth", type=int, default=16, help="frames in flight in the streaming analyzer")
     ap.add_argument("--equal-shards", action="store_true",
@@ -537,16 +537,34 @@ def main():
         # Ingest-proportional shards (N > 1): the GPUs of one box do not see the same host link -- with eight ranks
         # uploading, four B200s of the pool's boxes receive 23-25 GB/s and four 35-39 GB/s (profiles/r2_n_h2d_numa_probe.json)
         # -- and with equal shards the slow ranks set the pace.  Every rank takes a share of the step's
-        # world * frames_per_step frames proportional to the upload rate it has just measured, so all ranks finish
-        # together; the work of the whole job per step is unchanged.  --equal-shards keeps 32 frames per rank.
+        # world * frames_per_step frames proportional to the frame rate it reaches in two short untimed passes with all
+        # ranks running (equal shares first, then the shares that gave), so all ranks finish together; the work of
+        # the whole job per step is unchanged.  --equal-shards keeps 32 frames per rank.
         e2e_fps = fps
         e2e_fps_all = [fps] * world
         if world > 1 and not args.equal_shards:
-            rates = torch.zeros(world, dtype=torch.float64, device="cuda")
-            rates[rank] = h2d_gbs
-            dist.all_reduce(rates)
-            share = (rates / rates.sum()).cpu().numpy()
-            e2e_fps_all = [max(8, int(round(fps * world * float(x)))) for x in share]
+            def measured_rates(fps_r: int):
+                """frames/s of every rank for one untimed 2-step e2e pass with fps_r frames per step on this rank,
+                all ranks running at once (what the shares are proportional to)."""
+                barrier()
+                ctx.mark(2)
+                one_pass(2, capi.PC_MEM_HOST_PINNED, host_ptr, ring, True, Sweep(ring) if track else None, False, fps_r)
+                ctx.mark(3)
+                ctx.synchronize()
+                ctx.analyze_end()
+                r = torch.zeros(world, dtype=torch.float64, device="cuda")
+                r[rank] = (halo + 2 * fps_r) / max(ctx.elapsed_ms(2, 3), 1e-3)
+                dist.all_reduce(r)
+                return r.cpu().numpy()
+
+            def shares(rates):
+                out = [max(8, int(round(fps * world * float(x) / float(rates.sum())))) for x in rates]
+                return out
+
+            one_pass(1, capi.PC_MEM_HOST_PINNED, host_ptr, ring, True, Sweep(ring) if track else None, False, fps)   # first-touch costs
+            ctx.analyze_end()
+            e2e_fps_all = shares(measured_rates(fps))                       # from equal shards ...
+            e2e_fps_all = shares(measured_rates(e2e_fps_all[rank]))         # ... refined once under the new load
             e2e_fps = e2e_fps_all[rank]
         e2e_res = timed_leg(capi.PC_MEM_HOST_PINNED, host_ptr, ring, download=True, fps=e2e_fps)
         if args.diag and rank == 0:
@@ -598,7 +616,7 @@ def main():
                        "h2d_bytes_per_step": int(frame_bytes * sum(e2e_fps_all) / world),
                        "frames_per_step_per_rank": e2e_fps_all,
                        "sharding": ("equal shards" if len(set(e2e_fps_all)) == 1 else
-                                    "shares of the step's frames proportional to each rank's measured upload rate"),
+                                    "shares of the step's frames proportional to each rank's measured e2e frame rate (two untimed calibration passes)"),
                        "d2h_bytes_per_step": int(rows_per_step * 16 + fps * max_corners * 8),
                        "wall_s": e2e["wall_s"], "clocks": e2e["clocks"],
                        "h2d_pinned_gbs_per_gpu": {"min": reduce_min(h2d_gbs), "max": reduce_max(h2d_gbs),

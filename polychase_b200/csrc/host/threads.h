@@ -13,12 +13,14 @@
 #include <chrono>
 #include <condition_variable>
 #include <deque>
+#include <functional>
 #include <memory>
 #include <mutex>
 #include <optional>
 #include <string>
 #include <thread>
 #include <variant>
+#include <vector>
 
 #include "pipelines.h"
 
@@ -120,6 +122,67 @@ class PinnedFrameRing {
     bool failed_ = false;
 };
 
+// Persistent helper threads for the frame hand-off copy: a 4K RGB frame is 25 MB, and one core copies about
+// 10 GB/s.  (Spawning threads per frame, as the first version did, costs ~0.2 ms of the ~1.5 ms.)
+class CopyPool {
+   public:
+    explicit CopyPool(int helpers) {
+        for (int i = 0; i < helpers; i++) threads_.emplace_back([this, i] { Run(i); });
+    }
+    ~CopyPool() {
+        {
+            std::lock_guard<std::mutex> lk(mtx_);
+            quit_ = true;
+            generation_++;
+        }
+        cv_.notify_all();
+        for (auto& t : threads_) t.join();
+    }
+    int parts() const { return (int)threads_.size() + 1; }
+    // fn(part) for part = 0 .. parts()-1, part 0 on the calling thread; returns when all are done
+    void Run(const std::function<void(int)>& fn) {
+        {
+            std::lock_guard<std::mutex> lk(mtx_);
+            fn_ = &fn;
+            pending_ = (int)threads_.size();
+            generation_++;
+        }
+        cv_.notify_all();
+        fn(0);
+        std::unique_lock<std::mutex> lk(mtx_);
+        done_cv_.wait(lk, [&] { return pending_ == 0; });
+        fn_ = nullptr;
+    }
+
+   private:
+    void Run(int index) {
+        uint64_t seen = 0;
+        for (;;) {
+            const std::function<void(int)>* fn;
+            {
+                std::unique_lock<std::mutex> lk(mtx_);
+                cv_.wait(lk, [&] { return generation_ != seen; });
+                seen = generation_;
+                if (quit_) return;
+                fn = fn_;
+            }
+            (*fn)(index + 1);
+            {
+                std::lock_guard<std::mutex> lk(mtx_);
+                pending_--;
+            }
+            done_cv_.notify_one();
+        }
+    }
+    std::vector<std::thread> threads_;
+    std::mutex mtx_;
+    std::condition_variable cv_, done_cv_;
+    const std::function<void(int)>* fn_ = nullptr;
+    int pending_ = 0;
+    uint64_t generation_ = 0;
+    bool quit_ = false;
+};
+
 class OpticalFlowThread {
    public:
     OpticalFlowThread(VideoInfo video_info, std::string database_path, GFTTOptions detector_options = {},
@@ -163,19 +226,18 @@ class OpticalFlowThread {
             f.keep_alive = buf;
         }
         f.data = dst;
-        // 4K RGB is 25 MB: split the copy over a few threads
-        const int parts = bytes >= (8u << 20) ? 4 : 1;
+        // 4K RGB is 25 MB: split the copy over the pool (7 helpers + this thread)
         auto copy_rows = [&](int y0, int y1) {
             if (stride == row) memcpy(dst + (size_t)y0 * row, rgb + (size_t)y0 * row, (size_t)(y1 - y0) * row);
             else for (int y = y0; y < y1; y++) memcpy(dst + (size_t)y * row, rgb + (size_t)y * stride, row);
         };
-        if (parts == 1) {
+        if (bytes < (8u << 20)) {
             copy_rows(0, height);
         } else {
-            std::thread helpers[3];
-            for (int k = 1; k < parts; k++) helpers[k - 1] = std::thread(copy_rows, height * k / parts, height * (k + 1) / parts);
-            copy_rows(0, height / parts);
-            for (auto& t : helpers) t.join();
+            if (!pool_) pool_ = std::make_unique<CopyPool>(7);
+            const int parts = pool_->parts();
+            const std::function<void(int)> job = [&](int k) { copy_rows((int)((int64_t)height * k / parts), (int)((int64_t)height * (k + 1) / parts)); };
+            pool_->Run(job);
         }
         {
             std::lock_guard<std::mutex> lk(frame_mtx_);
@@ -228,6 +290,7 @@ class OpticalFlowThread {
     ResultQueue<OpticalFlowThreadMessage> queue_;
     std::optional<std::pair<int32_t, Frame>> provided_;
     PinnedFrameRing ring_;       // touched by the providing thread only
+    std::unique_ptr<CopyPool> pool_;   // likewise
     std::mutex frame_mtx_;
     std::condition_variable frame_cv_;
     bool stop_ = false;

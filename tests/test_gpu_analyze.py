@@ -304,12 +304,16 @@ def _stream_rows(ctx, w, h, frames, max_corners):
 
 
 @pytest.mark.parametrize("env", [{"PC_LK_QUEUE": "1"}, {"PC_LK_QUEUE": "1", "PC_LK_BUDGET": "24"},
-                                 {"PC_LK_QUEUE": "1", "PC_LK_BUDGET": "100"}])
+                                 {"PC_LK_QUEUE": "1", "PC_LK_BUDGET": "100"},
+                                 {"PC_DET_STREAMS": "1", "PC_LK_STREAMS": "1"}, {"PC_DET_STREAMS": "1"}, {"PC_LK_STREAMS": "1"},
+                                 {"PC_LK_STREAM": "0"}])
 def test_lk_work_queue_schedules_agree(ctx_small, env, monkeypatch):
     """The 10x10 LK can run as a work queue (lk10q.cu, PC_LK_QUEUE=1: a pentad takes the next (pair, keypoint) as
     soon as it is done) -- a change of schedule only.  Every schedule (the default lock-step kernel = the session
     context, queue with resident blocks, queue with blocks that leave after 24 or 100 items) must give the same
-    rows, bit for bit; one pair is also compared with the oracle."""
+    rows, bit for bit; one pair is also compared with the oracle.  The same holds for the stream layout: the session
+    context runs two detector and two LK streams (frames / batches alternate, csrc/abi/capi.cu); one of each, and
+    everything on one stream (PC_LK_STREAM=0), must give identical rows."""
     from polychase_b200 import capi
     w, h, F = 640, 480, 11
     clip = synth.Clip(w, h, F, seed=77, first_frame=0)
