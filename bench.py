@@ -675,6 +675,11 @@ def main():
                 issue = {"bound": "issue", "warp_inst_per_launch": ent["warp_inst_per_launch"],
                          "achieved_ginst_s": ach_inst / 1e9, "peak_ginst_s": peak_inst / 1e9,
                          "frac": ach_inst / peak_inst,
+                         # the live span covers the launch while it shares the chip with the other LK stream and the
+                         # detector streams; alone (committed launch list) the kernel issues at this fraction of the roof
+                         "frac_isolated": (ent["warp_inst_per_launch"] / (ent["isolated_us"] * 1e-6) / peak_inst
+                                           if ent.get("isolated_us") else None),
+                         "isolated_us": ent.get("isolated_us"),
                          "active_lanes_per_inst": ent.get("thread_inst_per_inst"), "source": ent.get("source")}
     except Exception:
         traffic = issue = None
