@@ -129,3 +129,81 @@ def test_4k_detector_equals_cv2_exact_eig_lists(ctx_4k):
         eig = ctx_4k.min_eig_map(300 + i, W, H)
         assert (eig != e1).sum() <= 40                       # a handful of 1..32-ulp tie flips per 8.3 Mpx frame
         ctx_4k.release(300 + i)
+
+
+def test_4k_track_and_refine_recover_the_truth(ctx_4k):
+    """BASELINE configs[2] / [4] shapes through size-independent properties (the oracle's numpy refine does not
+    finish a 4K x 8000-feature problem in seconds): a 40-frame 4K clip with the survey's motion, rendered on the
+    device, is analyzed with the fused forward Track sweep (tracker.cc:133-192) and then refined (refiner.cc:680-725)
+    from a perturbed trajectory.  Properties: the sweep's poses stay within 1e-4 relative of the synthetic ground
+    truth (translation, against the scene depth); refine's final cost is the ground truth's cost to 1e-3 and never
+    above the initial cost; the refined trajectory is within 1e-4 relative of the truth; the edge set is the
+    8F - 30 pairs of GenerateOpticalFlowDatabase."""
+    from polychase_b200 import capi
+    from polychase_b200 import synth as psynth
+    F, depth = 40, 4.0
+    speed = psynth.survey_speed(W)
+    K = psynth.intrinsics(W, H)
+    scale = psynth.plane_scale(W, depth)
+    Rs, ts = psynth.camera_path(F, depth, 0, speed)
+    verts, tris = psynth.plane_mesh(W, H, scale)
+    ctx_4k.synth_set_texture(psynth.make_texture(W, H, seed=0))
+    frame_bytes = W * H * 3
+    dev = ctx_4k.device_alloc(frame_bytes * F)
+    try:
+        for i in range(F):
+            ctx_4k.synth_render(psynth.homography(K, Rs[i], ts[i], W, H, scale), dev + i * frame_bytes, W * 3)
+        ctx_4k.synchronize()
+        truth = [capi.camera_state(K, Rs[i], ts[i]) for i in range(F)]
+        ctx_4k.mesh_set(verts, tris)
+        ctx_4k.analyze_begin(W, H, 0, F, capi.default_gftt(max_corners=N), capi.default_flow())
+        ctx_4k.analyze_track_begin(np.eye(4, dtype=np.float32), capi.default_bundle(loss_type=2))
+        ctx_4k.analyze_track_seed(0, truth[0])
+        kps, flows, poses = {}, {}, {}
+
+        def take(r):
+            kps[r["frame_id"]] = np.array(r["keypoints"], np.float32).reshape(-1, 2).copy()
+            for (a, b, rows, idx, tgt, err) in r["pairs"]:
+                flows[(a, b)] = (np.array(idx, np.uint32).copy(), np.array(tgt, np.float32).reshape(-1, 2).copy())
+            if r["tracked"] == 1:
+                poses[r["frame_id"]] = np.array(r["camera"].t[:], np.float64)
+
+        for i in range(F):
+            ctx_4k.analyze_push(i, dev + i * frame_bytes, W * 3, capi.PC_MEM_DEVICE)
+            if ctx_4k.analyze_pending() >= 4:
+                take(ctx_4k.analyze_pop(download=True, copy=True))
+        while ctx_4k.analyze_pending():
+            take(ctx_4k.analyze_pop(download=True, copy=True))
+        ctx_4k.analyze_end()
+    finally:
+        ctx_4k.device_free(dev)
+    assert len(flows) == 8 * F - 30 and len(kps) == F
+    assert len(poses) == F - 1                                   # every frame after the seeded one was solved
+    sweep_err = max(np.abs(poses[k] - ts[k]).max() for k in poses)
+    assert sweep_err < 1e-4 * depth, sweep_err
+    # ---- refine from a perturbed trajectory ---------------------------------------------------------------
+    edges = [(a, b, flows[(a, b)][0], flows[(a, b)][1]) for (a, b) in sorted(flows) if len(flows[(a, b)][0])]
+    assert sum(len(e[2]) for e in edges) > 0.9 * N * (8 * F - 30)
+    ctx_4k.ba_load([kps[k] for k in range(F)], edges, np.eye(4, dtype=np.float32), False, False)
+    rng = np.random.default_rng(1)
+    traj = []
+    for i in range(F):
+        R, t = Rs[i], ts[i]
+        if 0 < i < F - 1:
+            wv = rng.normal(0, np.deg2rad(0.2), 3)
+            th = np.linalg.norm(wv)
+            kx = np.array([[0, -wv[2], wv[1]], [wv[2], 0, -wv[0]], [-wv[1], wv[0], 0]])
+            R = R @ (np.eye(3) + (np.sin(th) / th) * kx + ((1 - np.cos(th)) / th ** 2) * (kx @ kx))
+            t = t + rng.normal(0, 0.005 * depth, 3)
+        traj.append(capi.camera_state(K, R, t))
+
+    def pose_err(tr):
+        return max(float(np.abs(np.array(tr[i].t[:]) - ts[i]).max()) for i in range(F))
+
+    bo = capi.default_bundle(loss_type=2, max_iterations=20)
+    truth_cost = ctx_4k.ba_cost(truth, bo)
+    assert pose_err(traj) > 0.01
+    out, st = ctx_4k.ba_solve(traj, bo)
+    assert st.cost <= st.initial_cost
+    assert abs(st.cost - truth_cost) <= 1e-3 * truth_cost, (st.cost, truth_cost)
+    assert pose_err(out) < 1e-4 * depth, pose_err(out)
