@@ -1249,7 +1249,10 @@ int pc_host_alloc_pinned(pc_ctx* c, size_t bytes, void** out) {
     const int node = numa ? device_numa_node(c->device) : -1;
     bool policy_set = false;
 #ifdef __linux__
-    if (node >= 0 && node < 64) {
+    int saved_mode = 0;                                   // the calling thread's own policy is put back afterwards
+    unsigned long saved_mask[16] = {0};                   // up to 1024 nodes
+    if (node >= 0 && node < 64 &&
+        syscall(SYS_get_mempolicy, &saved_mode, saved_mask, sizeof(saved_mask) * 8ul, nullptr, 0ul) == 0) {
         unsigned long mask = 1ul << node;
         policy_set = syscall(SYS_set_mempolicy, 1 /* MPOL_PREFERRED */, &mask, 64ul) == 0;
     }
@@ -1259,7 +1262,8 @@ int pc_host_alloc_pinned(pc_ctx* c, size_t bytes, void** out) {
     static const bool wc = getenv("PC_PINNED_WC") != nullptr && atoi(getenv("PC_PINNED_WC")) != 0;
     const cudaError_t e = cudaHostAlloc(out, bytes, wc ? cudaHostAllocWriteCombined : cudaHostAllocDefault);
 #ifdef __linux__
-    if (policy_set) syscall(SYS_set_mempolicy, 0 /* MPOL_DEFAULT */, nullptr, 0ul);
+    if (policy_set && syscall(SYS_set_mempolicy, saved_mode, saved_mask, sizeof(saved_mask) * 8ul) != 0)
+        syscall(SYS_set_mempolicy, 0 /* MPOL_DEFAULT */, nullptr, 0ul);
 #endif
     PC_CUDA(c, e);
     return PC_OK;
