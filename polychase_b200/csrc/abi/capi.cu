@@ -105,6 +105,7 @@ static FrameSlot* acquire_slot(pc_ctx* c, int32_t frame_id) {
     s->stamp = ++c->stamp;
     s->has_kps = false;
     s->has_tmpl = false;
+    s->has_order = false;
     s->n_kps_host = -1;
     return s;
 }
@@ -260,6 +261,7 @@ static void fill_pair(pc_ctx* c, LKPair& p, const FrameSlot& a, const FrameSlot&
     p.b = view_of(b);
     p.tmpl = LKTemplates{nullptr, nullptr, 0};
     if (use_templates && a.has_tmpl) p.tmpl = LKTemplates{a.tmpl, a.tmpl_queue_layout ? nullptr : a.tmpl_sums, cap};
+    p.order = (use_templates && a.has_tmpl && a.has_order) ? a.order : nullptr;
     p.pts = a.kps;
     p.n_pts = a.n_kps;
     p.next = (second_set ? c->lk_next2 : c->lk_next) + (size_t)k * cap * 2;
@@ -347,7 +349,7 @@ pc_ctx::~pc_ctx() {
         cudaFree(s.tmpl);
         cudaFree(s.tmpl_sums);
         cudaFree(s.base);
-        cudaFree(s.kps); cudaFree(s.n_kps);
+        cudaFree(s.kps); cudaFree(s.n_kps); cudaFree(s.order);
     }
     cudaFree(eig); cudaFree(state); cudaFree(cell_max); cudaFree(cand); cudaFree(det_zero);
     cudaFree(sel.accepted); cudaFree(sel.sorted); cudaFree(sel.cub_temp); cudaFree(sel.strong); cudaFree(sel.bin_start);
@@ -500,6 +502,7 @@ int pc_create(const pc_limits* limits, pc_ctx** out) {
             s.level[L].pitch = pitches[L];
         }
         PC_CUDA(nullptr, cudaMalloc(&s.kps, sizeof(float) * 2 * cap));
+        PC_CUDA(nullptr, cudaMalloc(&s.order, sizeof(int) * (size_t)cap));
         PC_CUDA(nullptr, cudaMalloc(&s.n_kps, sizeof(int) * 4));
         PC_CUDA(nullptr, cudaMemset(s.n_kps, 0, sizeof(int) * 4));
         s.n_accepted = s.n_kps + 1;
@@ -818,7 +821,7 @@ int pc_analyze_begin(pc_ctx* c, const pc_video_info* vi, const pc_gftt_opts* go,
             }
         }
     }
-    for (auto& s : c->slots) { s.used = false; s.has_tmpl = false; }
+    for (auto& s : c->slots) { s.used = false; s.has_tmpl = false; s.has_order = false; }
     // template cache of the 10x10 LK kernel: (max_level + 1) x max_features x 640 B per slot, kept as
     // long as it stays under 4 GB for the whole ring (the kernel computes templates itself otherwise)
     {
@@ -947,11 +950,19 @@ static int enqueue_lk(pc_ctx* c, Stage& st, FrameSlot* f) {
     // source templates of this frame's keypoints (once per frame; its eight pairs load them)
     if (f->tmpl && lkp.win == 10 && lkp.max_level + 1 <= f->tmpl_levels) {
         span_begin(c, KF_LK_TMPL, lks);
+        // PC_LK_SPATIAL=0: walk the keypoints in index (strength) order
+        static const bool spatial = getenv("PC_LK_SPATIAL") == nullptr || atoi(getenv("PC_LK_SPATIAL")) != 0;
+        f->has_order = false;
+        if (spatial && !c->lk_queue_mode && f->order) {
+            launch_spatial_order(f->kps, f->n_kps, c->lim.max_features, f->w, f->h, f->order, lks);
+            f->has_order = true;
+        }
         if (c->lk_queue_mode) launch_lk10q_templates(view_of(*f), f->kps, f->n_kps, c->lim.max_features, lkp, f->tmpl, lks);
-        else launch_lk10_templates(view_of(*f), f->kps, f->n_kps, c->lim.max_features, lkp, f->tmpl, f->tmpl_sums, lks);
+        else launch_lk10_templates(view_of(*f), f->kps, f->n_kps, c->lim.max_features, lkp, f->tmpl, f->tmpl_sums, lks,
+                                   f->has_order ? f->order : nullptr);
         f->tmpl_queue_layout = c->lk_queue_mode;
         span_end(c, lks);
-        rc = check_launch(c, "lk templates", 1);
+        rc = check_launch(c, "lk templates", f->has_order ? 2 : 1);
         if (rc) return rc;
         f->has_tmpl = true;
         if (c->side) {

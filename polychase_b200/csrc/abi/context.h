@@ -34,6 +34,8 @@ struct FrameSlot {
     int tmpl_levels = 0;          // levels the allocation holds
     bool has_tmpl = false;        // computed for the frame and keypoints the slot holds now
     bool tmpl_queue_layout = false;   // which kernel wrote them (lk10q.cu's layout or lk10.cu's)
+    int* order = nullptr;             // spatial order of the keypoints (launch_spatial_order), valid with has_tmpl
+    bool has_order = false;
 };
 
 enum KernelFamily { KF_GRAY_PYR = 0, KF_MIN_EIG, KF_SELECT, KF_LK, KF_COMPACT, KF_RAYCAST, KF_PNP, KF_BA, KF_LK_TMPL, KF_COUNT };

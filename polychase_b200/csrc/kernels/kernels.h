@@ -103,6 +103,8 @@ struct LKPair {
     LKTemplates tmpl;
     const float* pts;            // source keypoints (x,y)
     const int* n_pts;            // device count
+    const int* order;            // optional: the order in which lk10_kernel walks the source keypoints (a permutation
+                                 // of 0..n-1, spatially sorted: launch_spatial_order); nullptr = index order
     float* next;                 // dense outputs, capacity `cap`
     uint8_t* status;
     float* err;
@@ -124,7 +126,12 @@ void launch_lk(const LKBatch& batch, const LKParams& p, cudaStream_t s);
 void launch_lk_compact(const LKBatch& batch, cudaStream_t s);
 // Templates of frame `a`'s keypoints for every level the 10x10 kernel will visit (win must be 10).
 void launch_lk10_templates(const PyramidView& a, const float* pts, const int* n_pts, int cap, const LKParams& p,
-                           uint4* words, float* sums, cudaStream_t s);
+                           uint4* words, float* sums, cudaStream_t s, const int* order = nullptr);
+// order[0..n) = the keypoints' indices sorted by 64 x 64-pixel cell (row-major cells; the order inside a cell is
+// arbitrary).  The LK kernels use it only to decide which keypoints share a warp / a block -- results are written by
+// keypoint index, so it cannot change them: neighbours in the image read the same cache lines and, for the +-8 pairs,
+// tend to need similar iteration counts.  One block; scratch = 2 * kSpatialCellsMax ints are taken from shared memory.
+void launch_spatial_order(const float* pts, const int* n_pts, int cap, int w, int h, int* order, cudaStream_t s);
 // The same in the queue layout (kLkQueueTemplateBytesPerPoint per level and point).
 void launch_lk10q_templates(const PyramidView& a, const float* pts, const int* n_pts, int cap, const LKParams& p,
                             uint4* words, cudaStream_t s);

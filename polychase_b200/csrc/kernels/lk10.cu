@@ -50,16 +50,18 @@ using namespace lk10;
 __global__ void __launch_bounds__(LK_WARPS * 32, 4) lk10_template_kernel(PyramidView a, const float* __restrict__ pts,
                                                                          const int* __restrict__ n_pts, int cap, int nlev,
                                                                          uint4* __restrict__ words,
-                                                                         float* __restrict__ sums) {
+                                                                         float* __restrict__ sums,
+                                                                         const int* __restrict__ order) {
     const int level = blockIdx.y;
     if (level >= min(a.levels, nlev)) return;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int grp = lane / PENTAD, role = lane - grp * PENTAD;
     const int base = grp < PTS_PER_WARP ? grp * PENTAD : 0;
     const int npts = min(*n_pts, cap);
-    const int pi = (blockIdx.x * LK_WARPS + wib) * PTS_PER_WARP + grp;
-    const bool valid = grp < PTS_PER_WARP && pi < npts;
+    const int slot = (blockIdx.x * LK_WARPS + wib) * PTS_PER_WARP + grp;
+    const bool valid = grp < PTS_PER_WARP && slot < npts;
     if (!__any_sync(FULL, valid)) return;
+    const int pi = (valid && order) ? __ldg(order + slot) : slot;      // which keypoint this pentad works on
     const int simd_flag = role < 4 ? 1 : 0;
     const int xa = simd_flag ? role : 8;
     float ptx = 0.f, pty = 0.f;
@@ -112,9 +114,10 @@ __global__ void __launch_bounds__(LK_WARPS * 32, CACHED ? LK_CACHED_BLOCKS : 4) 
     const int grp = lane / PENTAD, role = lane - grp * PENTAD;
     const int base = grp < PTS_PER_WARP ? grp * PENTAD : 0;       // first lane of this pentad (shuffle source)
     const int npts = min(*pr.n_pts, batch.cap);
-    const int pi = (blockIdx.x * LK_WARPS + wib) * PTS_PER_WARP + grp;
-    const bool valid = grp < PTS_PER_WARP && pi < npts;
+    const int slot = (blockIdx.x * LK_WARPS + wib) * PTS_PER_WARP + grp;
+    const bool valid = grp < PTS_PER_WARP && slot < npts;
     if (!__any_sync(FULL, valid)) return;
+    const int pi = (valid && pr.order) ? __ldg(pr.order + slot) : slot;  // which keypoint this pentad works on
 
     const int simd_flag = role < 4 ? 1 : 0;
     const int xa = simd_flag ? role : 8;              // first column of the lane's chain (second: +4, tail +1)
@@ -153,15 +156,15 @@ __global__ void __launch_bounds__(LK_WARPS * 32, CACHED ? LK_CACHED_BLOCKS : 4) 
         if (CACHED) {
             A11 = 0.f; A12 = 0.f; A22 = 0.f;
             if (act) {
-                const size_t slot = (size_t)level * pr.tmpl.cap + pi;
-                const uint4* q = pr.tmpl.words + (slot * PENTAD + role) * 8;
+                const size_t tslot = (size_t)level * pr.tmpl.cap + pi;
+                const uint4* q = pr.tmpl.words + (tslot * PENTAD + role) * 8;
                 uint32_t wv[32];
 #pragma unroll
                 for (int k = 0; k < 8; k++) {
                     const uint4 v = __ldg(q + k);
                     wv[4 * k] = v.x; wv[4 * k + 1] = v.y; wv[4 * k + 2] = v.z; wv[4 * k + 3] = v.w;
                 }
-                const float4 sv = __ldg(reinterpret_cast<const float4*>(pr.tmpl.sums + slot * 4));
+                const float4 sv = __ldg(reinterpret_cast<const float4*>(pr.tmpl.sums + tslot * 4));
                 A11 = sv.x; A12 = sv.y; A22 = sv.z;
 #pragma unroll
                 for (int k = 0; k < 10; k++) { Ival[2 * k] = (int)(wv[k] & 0xffffu); Ival[2 * k + 1] = (int)(wv[k] >> 16); }
@@ -264,11 +267,70 @@ __global__ void __launch_bounds__(LK_WARPS * 32, CACHED ? LK_CACHED_BLOCKS : 4) 
 }  // namespace
 
 void launch_lk10_templates(const PyramidView& a, const float* pts, const int* n_pts, int cap, const LKParams& p,
-                           uint4* words, float* sums, cudaStream_t s) {
+                           uint4* words, float* sums, cudaStream_t s, const int* order) {
     const int per_block = LK_WARPS * PTS_PER_WARP;
     const int nlev = std::min(a.levels, p.max_level + 1);
     dim3 grid((cap + per_block - 1) / per_block, nlev);
-    lk10_template_kernel<<<grid, LK_WARPS * 32, 0, s>>>(a, pts, n_pts, cap, p.max_level + 1, words, sums);
+    lk10_template_kernel<<<grid, LK_WARPS * 32, 0, s>>>(a, pts, n_pts, cap, p.max_level + 1, words, sums, order);
+}
+
+
+// ---- spatial order of a frame's keypoints (counting sort by 64 x 64-pixel cell) ---------------------------------
+namespace {
+constexpr int kSpatialCellsMax = 8192;
+__global__ void __launch_bounds__(1024) spatial_order_kernel(const float* __restrict__ pts, const int* __restrict__ n_pts, int cap,
+                                                             int w, int h, int shift, int* __restrict__ order) {
+    __shared__ int s_count[kSpatialCellsMax];
+    __shared__ int s_warp[32];
+    const int n = min(*n_pts, cap);
+    const int ncx = ((w - 1) >> shift) + 1, ncy = ((h - 1) >> shift) + 1, ncell = ncx * ncy;
+    for (int c = threadIdx.x; c < ncell; c += blockDim.x) s_count[c] = 0;
+    __syncthreads();
+    auto cell_of_pt = [&](int i) {
+        const int x = min(max(__float2int_rd(pts[2 * i]), 0), w - 1), y = min(max(__float2int_rd(pts[2 * i + 1]), 0), h - 1);
+        return (y >> shift) * ncx + (x >> shift);
+    };
+    for (int i = threadIdx.x; i < n; i += blockDim.x) atomicAdd(&s_count[cell_of_pt(i)], 1);
+    __syncthreads();
+    // exclusive scan of the cell counts, in place: every thread owns a contiguous run of cells
+    const int per = (ncell + blockDim.x - 1) / blockDim.x;
+    const int c0 = threadIdx.x * per, c1 = min(c0 + per, ncell);
+    int mine = 0;
+    for (int c = c0; c < c1; c++) mine += s_count[c];
+    int incl = mine;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += v;
+    }
+    if (lane == 31) s_warp[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+        int v = s_warp[lane], t = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int u = __shfl_up_sync(0xffffffffu, t, d);
+            if (lane >= d) t += u;
+        }
+        s_warp[lane] = t - v;                       // exclusive prefix of the warps
+    }
+    __syncthreads();
+    int run = s_warp[wid] + incl - mine;
+    for (int c = c0; c < c1; c++) {
+        const int k = s_count[c];
+        s_count[c] = run;                            // becomes the cell's fill cursor
+        run += k;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) order[atomicAdd(&s_count[cell_of_pt(i)], 1)] = i;
+}
+}  // namespace
+
+void launch_spatial_order(const float* pts, const int* n_pts, int cap, int w, int h, int* order, cudaStream_t s) {
+    int shift = 6;                                    // 64-pixel cells, coarser while there would be too many of them
+    while ((((w - 1) >> shift) + 1) * (((h - 1) >> shift) + 1) > kSpatialCellsMax) shift++;
+    spatial_order_kernel<<<1, 1024, 0, s>>>(pts, n_pts, cap, w, h, shift, order);
 }
 
 void launch_lk10q(const LKBatch& batch, const LKParams& p, cudaStream_t s);   // lk10q.cu

@@ -129,6 +129,8 @@ __device__ __forceinline__ void bar_init(uint64_t* bar) {
 }
 __device__ __forceinline__ void bulk_load(uint4* dst, const uint4* src, uint64_t* bar) {
     constexpr uint32_t bytes = QUADS * PENTAD * 16;
+    // the slot's previous contents were read through the generic proxy (LDS); order those reads before the async-proxy write
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(dst)),
                  "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(smem_addr(bar))
