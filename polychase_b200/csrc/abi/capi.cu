@@ -340,11 +340,12 @@ pc_ctx::~pc_ctx() {
     if (d2h) cudaStreamSynchronize(d2h);
     if (d2h_rows) cudaStreamSynchronize(d2h_rows);
     if (side) cudaStreamSynchronize(side);
-    if (compute2) cudaStreamSynchronize(compute2);
+    for (int k = 0; k < n_det_extra; k++) cudaStreamSynchronize(det_stream[k]);
     if (side2) cudaStreamSynchronize(side2);
     if (track && track->stream) cudaStreamSynchronize(track->stream);
     cudaFree(lk_next2); cudaFree(lk_status2); cudaFree(lk_err2);
-    if (det2) { free_det_scratch(*det2); delete det2; }
+    for (auto& d : det_set)
+        if (d) { free_det_scratch(*d); delete d; d = nullptr; }
     for (auto& s : slots) {
         cudaFree(s.tmpl);
         cudaFree(s.tmpl_sums);
@@ -381,8 +382,10 @@ pc_ctx::~pc_ctx() {
     if (ba) free_ba(ba);
     if (comm) free_comm(comm);
     if (side) cudaStreamDestroy(side);
-    if (compute2) cudaStreamDestroy(compute2);
-    if (join_d) cudaEventDestroy(join_d);
+    for (int k = 0; k < kMaxExtraDet; k++) {
+        if (det_stream[k]) cudaStreamDestroy(det_stream[k]);
+        if (det_join[k]) cudaEventDestroy(det_join[k]);
+    }
     if (side2) cudaStreamDestroy(side2);
     if (join_e) cudaEventDestroy(join_e);
     if (compute) cudaStreamDestroy(compute);
@@ -467,10 +470,12 @@ int pc_create(const pc_limits* limits, pc_ctx** out) {
             PC_CUDA(nullptr, cudaStreamCreateWithPriority(&cp->side2, cudaStreamNonBlocking, lo));
             PC_CUDA(nullptr, cudaEventCreateWithFlags(&cp->join_e, cudaEventDisableTiming));
         }
-        const char* d = getenv("PC_DET_STREAMS");   // PC_DET_STREAMS=1: one detector stream
-        if (cp->side && (!d || atoi(d) >= 2)) {
-            PC_CUDA(nullptr, cudaStreamCreateWithPriority(&cp->compute2, cudaStreamNonBlocking, hi < lo ? hi + 1 : lo));
-            PC_CUDA(nullptr, cudaEventCreateWithFlags(&cp->join_d, cudaEventDisableTiming));
+        const char* d = getenv("PC_DET_STREAMS");   // detector streams (1..4, default 3); 1: one detector stream
+        const int n_det = cp->side ? std::min(std::max(d ? atoi(d) : 3, 1), 1 + pc_ctx::kMaxExtraDet) : 1;
+        for (int k = 0; k + 1 < n_det; k++) {
+            PC_CUDA(nullptr, cudaStreamCreateWithPriority(&cp->det_stream[k], cudaStreamNonBlocking, hi < lo ? hi + 1 : lo));
+            PC_CUDA(nullptr, cudaEventCreateWithFlags(&cp->det_join[k], cudaEventDisableTiming));
+            cp->n_det_extra = k + 1;
         }
     }
     PC_CUDA(nullptr, cudaStreamCreateWithFlags(&cp->h2d, cudaStreamNonBlocking));
@@ -539,7 +544,7 @@ int pc_synchronize(pc_ctx* c) {
     PC_CUDA(c, cudaStreamSynchronize(c->d2h));
     PC_CUDA(c, cudaStreamSynchronize(c->d2h_rows));
     if (c->side) PC_CUDA(c, cudaStreamSynchronize(c->side));
-    if (c->compute2) PC_CUDA(c, cudaStreamSynchronize(c->compute2));
+    for (int k = 0; k < c->n_det_extra; k++) PC_CUDA(c, cudaStreamSynchronize(c->det_stream[k]));
     if (c->side2) PC_CUDA(c, cudaStreamSynchronize(c->side2));
     if (c->track && c->track->stream) PC_CUDA(c, cudaStreamSynchronize(c->track->stream));
     return PC_OK;
@@ -808,16 +813,18 @@ int pc_analyze_begin(pc_ctx* c, const pc_video_info* vi, const pc_gftt_opts* go,
             }
         }
     }
-    if (c->compute2) {
-        PC_CUDA(c, cudaStreamSynchronize(c->compute2));
-        if (!c->det2) {                              // the second detector stream's scratch set
-            c->det2 = new DetScratch();
-            int rc2 = alloc_det_scratch(c->lim.max_width, c->lim.max_height, *c->det2);
-            if (rc2) {                               // not enough memory: one detector stream
+    for (int k = 0; k < c->n_det_extra; k++) {
+        PC_CUDA(c, cudaStreamSynchronize(c->det_stream[k]));
+        if (!c->det_set[k]) {                        // the extra detector stream's scratch set
+            c->det_set[k] = new DetScratch();
+            int rc2 = alloc_det_scratch(c->lim.max_width, c->lim.max_height, *c->det_set[k]);
+            if (rc2) {                               // not enough memory: fewer detector streams
                 cudaGetLastError();
-                free_det_scratch(*c->det2);
-                delete c->det2;
-                c->det2 = nullptr;
+                free_det_scratch(*c->det_set[k]);
+                delete c->det_set[k];
+                c->det_set[k] = nullptr;
+                c->n_det_extra = k;
+                break;
             }
         }
     }
@@ -891,9 +898,9 @@ int pc_mark(pc_ctx* c, int slot) {
         PC_CUDA(c, cudaEventRecord(c->join_c, c->side));
         PC_CUDA(c, cudaStreamWaitEvent(c->compute, c->join_c, 0));
     }
-    if (c->compute2) {
-        PC_CUDA(c, cudaEventRecord(c->join_d, c->compute2));
-        PC_CUDA(c, cudaStreamWaitEvent(c->compute, c->join_d, 0));
+    for (int k = 0; k < c->n_det_extra; k++) {
+        PC_CUDA(c, cudaEventRecord(c->det_join[k], c->det_stream[k]));
+        PC_CUDA(c, cudaStreamWaitEvent(c->compute, c->det_join[k], 0));
     }
     if (c->side2) {
         PC_CUDA(c, cudaEventRecord(c->join_e, c->side2));
@@ -905,7 +912,7 @@ int pc_mark(pc_ctx* c, int slot) {
     }
     PC_CUDA(c, cudaEventRecord(c->marks[slot], c->compute));
     // work queued after the mark starts after it on every detector stream (a timed region opens with a mark)
-    if (c->compute2) PC_CUDA(c, cudaStreamWaitEvent(c->compute2, c->marks[slot], 0));
+    for (int k = 0; k < c->n_det_extra; k++) PC_CUDA(c, cudaStreamWaitEvent(c->det_stream[k], c->marks[slot], 0));
     return PC_OK;
 }
 
@@ -1052,8 +1059,9 @@ int pc_analyze_push_frame(pc_ctx* c, int32_t frame_id, const uint8_t* rgb, size_
 
     FrameSlot* f = acquire_slot(c, frame_id);
     // detector stream of this frame: frames alternate between the two (each owns a scratch set)
-    const bool second = c->compute2 && c->det2 && (c->pushed_count & 1);
-    cudaStream_t ds = second ? c->compute2 : c->compute;
+    const int det_turn = c->pushed_count % (1 + c->n_det_extra);     // 0 = `compute` and the primary set
+    const DetScratch* det_scratch = det_turn > 0 ? c->det_set[det_turn - 1] : nullptr;
+    cudaStream_t ds = (det_turn > 0 && det_scratch) ? c->det_stream[det_turn - 1] : c->compute;
     st.det_stream = ds;
     const uint8_t* dev = rgb;
     if (mem_kind != PC_MEM_DEVICE) {
@@ -1115,7 +1123,7 @@ int pc_analyze_push_frame(pc_ctx* c, int32_t frame_id, const uint8_t* rgb, size_
         f->n_kps_host = n;
         c->preset_kps.erase(preset);
     } else {
-        rc = run_detector(c, f, &c->gopts, ds, second ? c->det2 : nullptr);
+        rc = run_detector(c, f, &c->gopts, ds, ds == c->compute ? nullptr : det_scratch);
         if (rc) return rc;
     }
     st.is_halo = c->pushed_count < c->halo_frames;

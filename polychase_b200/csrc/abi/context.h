@@ -131,17 +131,19 @@ struct pc_ctx {
     // streaming analyzer: LK batches run on this low-priority stream next to the following frame's
     // pyramid + detector on `compute` (nullptr = everything on `compute`)
     cudaStream_t side = nullptr;
-    // second detector stream (+ scratch set, allocated by the first analyze pass): frames alternate between
-    // `compute` and `compute2`, so that one frame's latency-bound selection chain (a 16-CTA cluster) overlaps the
-    // next frame's pyramid / min-eig / NMS instead of serialising the detector.  PC_DET_STREAMS=1 disables it.
-    cudaStream_t compute2 = nullptr;
-    cudaEvent_t join_d = nullptr;
+    // extra detector streams (+ scratch sets, allocated by the first analyze pass): frames take `compute` and the
+    // extra streams in turn, so that one frame's latency-bound selection chain (a 16-CTA cluster) overlaps the next
+    // frames' pyramid / min-eig / NMS instead of serialising the detector.  PC_DET_STREAMS=n (1..4, default 3: resident throughput is the same from 2 up, e2e gains 1.8 % from the third, profiles/r2_y_det_streams_sweep.json).
+    static constexpr int kMaxExtraDet = 3;
+    int n_det_extra = 0;
+    cudaStream_t det_stream[kMaxExtraDet] = {nullptr, nullptr, nullptr};
+    cudaEvent_t det_join[kMaxExtraDet] = {nullptr, nullptr, nullptr};
+    pc::DetScratch* det_set[kMaxExtraDet] = {nullptr, nullptr, nullptr};
     // second LK stream (+ dense scratch set): the batches of consecutive frames alternate between `side` and `side2`,
     // so one batch's tail wave, template launch and compaction overlap the next batch.  PC_LK_STREAMS=1 disables it.
     cudaStream_t side2 = nullptr;
     cudaEvent_t join_e = nullptr;
     float* lk_next2 = nullptr; uint8_t* lk_status2 = nullptr; float* lk_err2 = nullptr;
-    pc::DetScratch* det2 = nullptr;
     std::string err;
     uint64_t launches = 0;
     uint64_t stamp = 0;
