@@ -1058,7 +1058,7 @@ int pc_analyze_push_frame(pc_ctx* c, int32_t frame_id, const uint8_t* rgb, size_
     st.num_pairs = 0;
 
     FrameSlot* f = acquire_slot(c, frame_id);
-    // detector stream of this frame: frames alternate between the two (each owns a scratch set)
+    // detector stream of this frame: frames take the streams in turn (each stream owns a scratch set)
     const int det_turn = c->pushed_count % (1 + c->n_det_extra);     // 0 = `compute` and the primary set
     const DetScratch* det_scratch = det_turn > 0 ? c->det_set[det_turn - 1] : nullptr;
     cudaStream_t ds = (det_turn > 0 && det_scratch) ? c->det_stream[det_turn - 1] : c->compute;
