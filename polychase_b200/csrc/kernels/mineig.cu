@@ -259,7 +259,6 @@ void launch_min_eig(Image8 gray, float* eig, int eig_pitch, DetectGrid g, int* c
 constexpr int NMS_ROWS = 16;
 constexpr int NMS_WARPS = 4;
 constexpr int NMS_MAX_CELLS = 1024;    // grid_rows * grid_cols limit (validated in csrc/abi/capi.cu)
-constexpr int NMS_STAGE = 512;         // candidate keys staged per warp before one global append
 
 __global__ void __launch_bounds__(NMS_WARPS * 32) nms_candidates_kernel(
     const float* __restrict__ eig, int eig_pitch, int w, int h, DetectGrid grid, const int* __restrict__ cell_max,
@@ -268,7 +267,6 @@ __global__ void __launch_bounds__(NMS_WARPS * 32) nms_candidates_kernel(
     const unsigned FULL = 0xffffffffu;
     __shared__ float thr_tab[NMS_MAX_CELLS];
     __shared__ int s_hist[4096];                              // block-private copy of value_hist
-    __shared__ unsigned long long s_stage[NMS_WARPS][NMS_STAGE];
     const int ncell = grid.grid_rows * grid.grid_cols;
     for (int i = threadIdx.x; i < ncell; i += blockDim.x)
         thr_tab[i] = (float)((double)ordered_int_to_float(__ldg(&cell_max[i])) * quality);
@@ -282,16 +280,7 @@ __global__ void __launch_bounds__(NMS_WARPS * 32) nms_candidates_kernel(
     const int xb = tx * 128 + 4 * lane;
     const int y0 = ty * NMS_ROWS, y_end = tile_ok ? min(y0 + NMS_ROWS, h) : y0;
     const bool live = tile_ok && xb < w;
-    int fill = 0;                                             // staged keys of this warp (warp-uniform)
-    auto flush = [&]() {
-        int base = 0;
-        if (lane == 0 && fill) base = atomicAdd(cand_count, fill);
-        base = __shfl_sync(FULL, base, 0);
-        for (int i = lane; i < fill; i += 32)
-            if (base + i < cand_cap) cand[base + i] = s_stage[wib][i];
-        __syncwarp();
-        fill = 0;
-    };
+    unsigned long long cbits = 0;                             // this lane's candidates of the tile: bit 4 * (y - y0) + j
     int cxj[6];                                   // cell column of x = xb-1 .. xb+4
 #pragma unroll
     for (int j = 0; j < 6; j++) cxj[j] = min(max(xb - 1 + j, 0), w - 1) / grid.block_w;
@@ -373,34 +362,40 @@ __global__ void __launch_bounds__(NMS_WARPS * 32) nms_candidates_kernel(
             else
                 for (int j = 0; j < 4 && xb + j < w; j++) sp[j] = (bits >> (8 * j)) & 1u;
         }
-        // stage the row's candidates in shared memory (order inside the list is irrelevant: keys are
-        // sorted later); one global append per warp tile
-        const int mine = (int)is_c[0] + (int)is_c[1] + (int)is_c[2] + (int)is_c[3];
-        if (__any_sync(FULL, mine > 0)) {
-            int incl = mine;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int n = __shfl_up_sync(FULL, incl, o);
-                if (lane >= o) incl += n;
-            }
-            const int total = __shfl_sync(FULL, incl, 31);
-            if (fill + total > NMS_STAGE) flush();
-            int slot = fill + incl - mine;
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                if (is_c[j]) {
-                    const uint32_t ov = float_to_ordered_uint(b[j + 1]);
-                    s_stage[wib][slot++] = ((unsigned long long)ov << 32) | (unsigned)(y * w + xb + j);
-                    atomicAdd(&s_hist[ov >> 20], 1);
-                }
-            }
-            fill += total;
-            __syncwarp();
-        }
+        // the row's candidates are only remembered here (4 bits per lane and row); they are appended once per tile
+        cbits |= (unsigned long long)((bits & 1u) | ((bits >> 7) & 2u) | ((bits >> 14) & 4u) | ((bits >> 21) & 8u)) << (4 * (y - y0));
 #pragma unroll
         for (int j = 0; j < 6; j++) { a[j] = b[j]; b[j] = c[j]; }
     }
-    flush();
+    // one append per warp tile (order inside the list is irrelevant: keys are sorted later): a warp scan of the
+    // lanes' counts, one atomic for the warp, then every lane writes its own keys -- the value of a candidate is its
+    // raw eigenvalue (it passed its threshold), re-read from the map (an L1 / L2 hit).  Appending row by row through a
+    // shared-memory stage cost a quarter of the kernel's instructions (profiles/r2_w_ncu_all_kernels_cold.txt).
+    static_assert(NMS_ROWS * 4 <= 64, "candidate bits of a tile fit one 64-bit word per lane");
+    const int mine = __popcll(cbits);
+    if (__any_sync(FULL, mine > 0)) {
+        int incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int n = __shfl_up_sync(FULL, incl, o);
+            if (lane >= o) incl += n;
+        }
+        const int total = __shfl_sync(FULL, incl, 31);
+        int base = 0;
+        if (lane == 0) base = atomicAdd(cand_count, total);
+        base = __shfl_sync(FULL, base, 0);
+        int slot = base + incl - mine;
+        while (cbits) {
+            const int bit = __ffsll((long long)cbits) - 1;
+            cbits &= cbits - 1;
+            const int y = y0 + (bit >> 2), x = xb + (bit & 3);
+            const uint32_t ov = float_to_ordered_uint(__ldg(eig + (size_t)y * eig_pitch + x));
+            if (slot < cand_cap) cand[slot] = ((unsigned long long)ov << 32) | (unsigned)(y * w + x);
+            slot++;
+            atomicAdd(&s_hist[ov >> 20], 1);
+        }
+        __syncwarp();
+    }
     }
     __syncthreads();
     for (int i = threadIdx.x; i < 4096; i += blockDim.x) {
@@ -420,7 +415,7 @@ void launch_nms_candidates(const float* eig, int eig_pitch, int w, int h, Detect
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
     }
-    blocks = std::min(blocks, sm_count * 6);                  // 36 KB of shared memory per block: 6 resident per SM
+    blocks = std::min(blocks, sm_count * 8);                  // persistent blocks (64 registers, 20 KB of shared memory each)
     nms_candidates_kernel<<<blocks, NMS_WARPS * 32, 0, s>>>(eig, eig_pitch, w, h, g, cell_max, quality_level, state,
                                                             state_pitch, cand, cand_cap, cand_count, value_hist,
                                                             tiles_x, tiles_y);
