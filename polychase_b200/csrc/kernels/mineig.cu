@@ -87,11 +87,9 @@ min_eig_kernel(const uint8_t* __restrict__ gray, int w, int h, int pitch, float*
     const bool left_tile = tile_x0 < 0, right_tile = tile_x0 + 32 * NC >= w;
 
     // grid cell bookkeeping: the common case is one cell column per warp tile
-    int cx[NC];
-#pragma unroll
-    for (int j = 0; j < NC; j++) cx[j] = min(max(xb + j, 0), w - 1) / grid.block_w;
-    const int cx_ref = __shfl_sync(FULL, cx[0], 1);
-    const bool my_uniform = !out_lane || (cx[0] == cx_ref && cx[NC - 1] == cx_ref);
+    const int cx_first = min(max(xb, 0), w - 1) / grid.block_w, cx_last = min(max(xb + NC - 1, 0), w - 1) / grid.block_w;
+    const int cx_ref = __shfl_sync(FULL, cx_first, 1);
+    const bool my_uniform = !out_lane || (cx_first == cx_ref && cx_last == cx_ref);
     const bool uniform_x = __all_sync(FULL, my_uniform);
     // eig >= -tiny and never NaN, so a float max is enough for the running cell maximum
     float run_max = -INFINITY;
@@ -131,8 +129,12 @@ min_eig_kernel(const uint8_t* __restrict__ gray, int w, int h, int pitch, float*
             const float pm = p[j], pc_ = p[j + 1], pp = p[j + 2];
             rx[2][j] = __fsub_rn(pp, pm);
             rsm[2][j] = __fmaf_rn(pp, s, __fmaf_rn(pc_, s2, __fmul_rn(pm, s)));
-            if (tail_tile && xb + j >= wvec)
-                rsm[2][j] = __fadd_rn(__fadd_rn(__fmul_rn(pm, s), __fmul_rn(pc_, s2)), __fmul_rn(pp, s));
+        }
+        if (tail_tile) {                                    // warp-uniform and rare: one branch, not 4 x 5 predicated slots
+#pragma unroll
+            for (int j = 0; j < NC; j++)
+                if (xb + j >= wvec)
+                    rsm[2][j] = __fadd_rn(__fadd_rn(__fmul_rn(p[j], s), __fmul_rn(p[j + 1], s2)), __fmul_rn(p[j + 2], s));
         }
         word = next_word;
         if (k < 2) continue;
@@ -150,8 +152,9 @@ min_eig_kernel(const uint8_t* __restrict__ gray, int w, int h, int pitch, float*
             c[1][j] = flip ? -xy : xy;
             c[2][j] = __fmul_rn(dy, dy);
         }
-        // ---- 3-tap horizontal sums in double, REFLECT_101 of cov at the image's side borders --
-        double R[3][NC];
+        // ---- 3-tap horizontal sums in double (REFLECT_101 of cov at the image's side borders), consumed at once by
+        // the 3-tap vertical sums: a row sum R only lives while its column is handled (fewer live doubles, fewer spills)
+        float sum3[3][NC];                                  // Sxx, Sxy, Syy of output row y = cy - 1, rounded once
 #pragma unroll
         for (int ch = 0; ch < 3; ch++) {
             double d[NC + 2];
@@ -166,18 +169,20 @@ min_eig_kernel(const uint8_t* __restrict__ gray, int w, int h, int pitch, float*
                     if (j == jr) d[j + 2] = d[j];
             }
 #pragma unroll
-            for (int j = 0; j < NC; j++) R[ch][j] = __dadd_rn(__dadd_rn(d[j], d[j + 1]), d[j + 2]);
+            for (int j = 0; j < NC; j++) {
+                const double R = __dadd_rn(__dadd_rn(d[j], d[j + 1]), d[j + 2]);
+                sum3[ch][j] = (float)__dadd_rn(T[ch][j], R);
+                T[ch][j] = __dadd_rn(Rp[ch][j], R);
+                Rp[ch][j] = R;
+            }
         }
-        // ---- 3-tap vertical sums, eigenvalue, store (output row y = cy - 1) --------------------
+        // ---- eigenvalue, store (output row y = cy - 1) -----------------------------------------------
         const int y = cy - 1;
         if (k >= 4) {
             float v[NC];
 #pragma unroll
             for (int j = 0; j < NC; j++) {
-                const float sxx = (float)__dadd_rn(T[0][j], R[0][j]);
-                const float sxy = (float)__dadd_rn(T[1][j], R[1][j]);
-                const float syy = (float)__dadd_rn(T[2][j], R[2][j]);
-                const float a = __fmul_rn(sxx, 0.5f), b = sxy, cc = __fmul_rn(syy, 0.5f);
+                const float a = __fmul_rn(sum3[0][j], 0.5f), b = sum3[1][j], cc = __fmul_rn(sum3[2][j], 0.5f);
                 const float t = __fsub_rn(a, cc);
                 v[j] = __fsub_rn(__fadd_rn(a, cc), __fsqrt_rn(__fadd_rn(__fmul_rn(t, t), __fmul_rn(b, b))));
             }
@@ -208,17 +213,11 @@ min_eig_kernel(const uint8_t* __restrict__ gray, int w, int h, int pitch, float*
                 } else {
 #pragma unroll
                     for (int j = 0; j < NC; j++)
-                        if (xb + j < w) atomicMax(&cell_max[run_cy * grid.grid_cols + cx[j]], float_to_ordered_int(v[j]));
+                        if (xb + j < w)                    // (the tile straddles a cell border: rare, the cell is found per pixel)
+                            atomicMax(&cell_max[run_cy * grid.grid_cols + (xb + j) / grid.block_w], float_to_ordered_int(v[j]));
                 }
             }
         }
-#pragma unroll
-        for (int ch = 0; ch < 3; ch++)
-#pragma unroll
-            for (int j = 0; j < NC; j++) {
-                T[ch][j] = __dadd_rn(Rp[ch][j], R[ch][j]);
-                Rp[ch][j] = R[ch][j];
-            }
     }
     if (uniform_x) {
         const int m = __reduce_max_sync(FULL, float_to_ordered_int(run_max));
