@@ -500,28 +500,72 @@ __global__ void __launch_bounds__(256) compact_top_kernel(const unsigned long lo
     }
 }
 
+// Ranks the keys of the short list inside their value bin and emits the first k as keypoints.  top[] holds the bins'
+// groups in descending bin order, unordered inside a group; a benchmark frame's 8 000 strongest corners fall into a
+// handful of 12-bit bins of ~2 000 keys each, so counting "greater keys of my bin" key by key (one warp per key: the
+// first version, 6.8 M warp instructions and the whole chip for 12 us) is quadratic where it hurts.  Here a block
+// takes a bin, splits it into 1024 sub-bins by the next ten bits of the value (shared-memory histogram, suffix sums,
+// one scatter into `scratch` -- the accepted[] buffer, dead by now), and a key then only compares itself with the
+// couple of keys of its own sub-bin: linear in the bin size.
+constexpr int RANK_SUB = 1024;
 __global__ void __launch_bounds__(256) select_rank_emit_kernel(
-    const unsigned long long* __restrict__ top, const int* __restrict__ sel, const int* __restrict__ kps_count,
-    const int* __restrict__ kept_hist, const int* __restrict__ bin_start, int w, float* __restrict__ kps) {
-    const int lane = threadIdx.x & 31;
+    const unsigned long long* __restrict__ top, unsigned long long* __restrict__ scratch, const int* __restrict__ sel,
+    const int* __restrict__ kps_count, const int* __restrict__ kept_hist, const int* __restrict__ bin_start, int w,
+    float* __restrict__ kps) {
+    __shared__ int s_cnt[RANK_SUB];                          // keys per sub-bin
+    __shared__ int s_cur[RANK_SUB];                          // fill cursors of the scatter
+    __shared__ int s_off[RANK_SUB];                          // keys of the bin in greater sub-bins
+    __shared__ int s_warp[8];
+    const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
     const int k = *kps_count;
-    const int m = sel[3];
-    const int warps = (gridDim.x * blockDim.x) >> 5;
-    for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < m; i += warps) {
-        const unsigned long long key = top[i];
-        const unsigned bin = (unsigned)(key >> 52);
-        const int g0 = __ldg(bin_start + bin), g1 = g0 + __ldg(kept_hist + bin);
-        int cnt = 0;
-        for (int j = g0 + lane; j < g1; j += 32) cnt += top[j] > key ? 1 : 0;
+    const int thr = sel[2];
+    if (k == 0) return;
+    for (int bin = TOP_BINS - 1 - (int)blockIdx.x; bin >= thr; bin -= (int)gridDim.x) {
+        const int g0 = __ldg(bin_start + bin), n = __ldg(kept_hist + bin);
+        if (n == 0 || g0 >= k) continue;                     // empty, or every key of it ranks behind the k-th (block-uniform)
+        for (int i = t; i < RANK_SUB; i += 256) { s_cnt[i] = 0; s_cur[i] = 0; }
+        __syncthreads();
+        for (int i = t; i < n; i += 256) atomicAdd(&s_cnt[(int)(top[g0 + i] >> 42) & (RANK_SUB - 1)], 1);
+        __syncthreads();
+        // suffix sums: thread t owns sub-bins [4 t, 4 t + 4)
+        int c4[4], own = 0;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-        const int rank = g0 + cnt;
-        if (lane == 0 && rank < k) {
-            const int addr = (int)(key & 0xffffffffu);
-            const int y = addr / w;
-            kps[2 * rank] = (float)(addr - y * w);
-            kps[2 * rank + 1] = (float)y;
+        for (int q = 0; q < 4; q++) { c4[q] = s_cnt[4 * t + q]; own += c4[q]; }
+        int v = own;                                         // suffix sum inside the warp (lanes >= lane)
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int nb = __shfl_down_sync(0xffffffffu, v, o);
+            if (lane + o < 32) v += nb;
         }
+        if (lane == 0) s_warp[wid] = v;
+        __syncthreads();
+        int above = 0;
+        for (int q = wid + 1; q < 8; q++) above += s_warp[q];
+        int run = v + above - own;                           // keys in sub-bins above this thread's
+#pragma unroll
+        for (int q = 3; q >= 0; q--) { s_off[4 * t + q] = run; run += c4[q]; }
+        __syncthreads();
+        for (int i = t; i < n; i += 256) {
+            const unsigned long long key = top[g0 + i];
+            const int sb = (int)(key >> 42) & (RANK_SUB - 1);
+            scratch[g0 + s_off[sb] + atomicAdd(&s_cur[sb], 1)] = key;
+        }
+        __syncthreads();                                     // (block-scope visibility of the scatter)
+        for (int i = t; i < n; i += 256) {
+            const unsigned long long key = scratch[g0 + i];
+            const int sb = (int)(key >> 42) & (RANK_SUB - 1);
+            const int r0 = s_off[sb], c = s_cnt[sb];
+            int cnt = 0;
+            for (int j = 0; j < c; j++) cnt += scratch[g0 + r0 + j] > key ? 1 : 0;
+            const int rank = g0 + r0 + cnt;
+            if (rank < k) {
+                const int addr = (int)(key & 0xffffffffu);
+                const int y = addr / w;
+                kps[2 * rank] = (float)(addr - y * w);
+                kps[2 * rank + 1] = (float)y;
+            }
+        }
+        __syncthreads();                                     // s_* are reused by the next bin
     }
 }
 
@@ -636,8 +680,8 @@ void launch_select(const unsigned long long* cand, const int* cand_count, int ca
         // the short list lives in the (otherwise unused on this path) sort output buffer
         compact_top_kernel<<<sm_count, 256, 0, s>>>(ws.accepted, ws.accepted_count, ws.kept_hist, max_corners, kps_cap,
                                                     ws.sorted, ws.sel, kps_count, ws.bin_cursor, ws.bin_start);
-        select_rank_emit_kernel<<<sm_count * 8, 256, 0, s>>>(ws.sorted, ws.sel, kps_count, ws.kept_hist, ws.bin_start, w,
-                                                             kps_out);
+        select_rank_emit_kernel<<<64, 256, 0, s>>>(ws.sorted, ws.accepted, ws.sel, kps_count, ws.kept_hist, ws.bin_start, w,
+                                                   kps_out);
     } else {
         size_t temp = ws.cub_temp_bytes;
         cub::DeviceRadixSort::SortKeysDescending(ws.cub_temp, temp, ws.accepted, ws.sorted, ws.cap, 0, 64, s);
