@@ -516,12 +516,21 @@ __global__ void __launch_bounds__(256) select_rank_emit_kernel(
     __shared__ int s_cur[RANK_SUB];                          // fill cursors of the scatter
     __shared__ int s_off[RANK_SUB];                          // keys of the bin in greater sub-bins
     __shared__ int s_warp[8];
+    __shared__ int s_g0[RANK_SUB / 16], s_n[RANK_SUB / 16];   // this block's bins: start and size (one round trip, not one per bin)
     const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
     const int k = *kps_count;
     const int thr = sel[2];
     if (k == 0) return;
-    for (int bin = TOP_BINS - 1 - (int)blockIdx.x; bin >= thr; bin -= (int)gridDim.x) {
-        const int g0 = __ldg(bin_start + bin), n = __ldg(kept_hist + bin);
+    const int my_bins = (TOP_BINS - 1 - (int)blockIdx.x - thr) / (int)gridDim.x + 1;     // bins of this block at or above thr
+    for (int i = t; i < RANK_SUB / 16; i += 256) {
+        const int bin = TOP_BINS - 1 - (int)blockIdx.x - i * (int)gridDim.x;
+        const bool in = i < my_bins && bin >= thr && bin >= 0;
+        s_g0[i] = in ? __ldg(bin_start + bin) : 0;
+        s_n[i] = in ? __ldg(kept_hist + bin) : 0;
+    }
+    __syncthreads();
+    for (int bi = 0; bi < min(my_bins, RANK_SUB / 16); bi++) {
+        const int g0 = s_g0[bi], n = s_n[bi];
         if (n == 0 || g0 >= k) continue;                     // empty, or every key of it ranks behind the k-th (block-uniform)
         for (int i = t; i < RANK_SUB; i += 256) { s_cnt[i] = 0; s_cur[i] = 0; }
         __syncthreads();
