@@ -16,7 +16,7 @@ import subprocess
 import sys
 
 rep, launches, key, src_ncu, src_list = sys.argv[1:6]
-FAMILIES = [("lk_tmpl", r"lk10q?_template_kernel"), ("lk", r"lk10q?_kernel|lk10q_err_kernel|lk_kernel"), ("compact", r"lk_compact_kernel"),
+FAMILIES = [("lk_tmpl", r"lk10q?_template_kernel|spatial_order_kernel"), ("lk", r"lk10q?_kernel|lk10q_err_kernel|lk_kernel"), ("compact", r"lk_compact_kernel"),
             ("gray_pyr", r"gray_l1_tma|l2_l3_tma|pad_border|rgb_to_gray|pyr_down"), ("min_eig", r"min_eig_kernel|init_cell_max"),
             ("select", r"nms_candidates|greedy_suppress|compact_top|select_rank"), ("raycast", r"raycast_"), ("pnp", r"pnp_lm_kernel")]
 
