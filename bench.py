@@ -57,6 +57,16 @@ CONFIGS = {
 SKIPS = (1, 2, 4, 8)
 
 
+def proportional_shares(rates, frames_per_step: int, floor: int = 8):
+    """Frames per step of every rank, proportional to its measured frame rate: the whole job keeps
+    len(rates) * frames_per_step frames per step (up to rounding); no rank gets fewer than `floor`."""
+    total = float(sum(rates))
+    n = len(rates)
+    if total <= 0.0:
+        return [frames_per_step] * n
+    return [max(floor, int(round(frames_per_step * n * float(r) / total))) for r in rates]
+
+
 def pairs_for_new_frame(idx_in_clip: int) -> int:
     """Directed pairs that become computable when frame `idx_in_clip` (0-based) arrives."""
     return 2 * sum(1 for d in SKIPS if idx_in_clip - d >= 0)
@@ -558,8 +568,7 @@ def main():
                 return r.cpu().numpy()
 
             def shares(rates):
-                out = [max(8, int(round(fps * world * float(x) / float(rates.sum())))) for x in rates]
-                return out
+                return proportional_shares([float(x) for x in rates], fps)
 
             one_pass(1, capi.PC_MEM_HOST_PINNED, host_ptr, ring, True, Sweep(ring) if track else None, False, fps)   # first-touch costs
             ctx.analyze_end()

@@ -25,3 +25,16 @@ def test_reference_arm_other_ranks_exit_quietly():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"],
                          capture_output=True, text=True, timeout=120, cwd=ROOT, env=env)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_proportional_shares_keep_the_work_of_the_job():
+    """bench.py's e2e leg at N > 1 sizes every rank's share of a step by its measured frame rate
+    (DESIGN.md section 8): equal rates give equal shares, the total stays N * frames_per_step up to
+    rounding, faster ranks get more, nobody drops below the floor."""
+    import bench
+    assert bench.proportional_shares([5.0, 5.0], 32) == [32, 32]
+    got = bench.proportional_shares([23.0, 23.1, 23.0, 23.1, 35.0, 35.1, 34.9, 35.2], 32)
+    assert abs(sum(got) - 8 * 32) <= 4 and got[0] < got[4] and min(got) >= 8
+    assert got == sorted(got) or got[:4] == sorted(got[:4])
+    assert bench.proportional_shares([1.0, 100.0], 32)[0] == 8
+    assert bench.proportional_shares([0.0, 0.0], 32) == [32, 32]
