@@ -430,3 +430,60 @@ def test_ba_empty_problem_returns_trajectory_unchanged(ctx_small, scene):
     got, st = ctx_small.ba_solve(traj, capi.default_bundle(loss_type=2, max_iterations=5))
     for k in range(NF):
         assert list(got[k].q) == list(traj[k].q) and list(got[k].t) == list(traj[k].t)
+
+
+def test_ray_cast_nearest_hit_with_occluders(ctx_small):
+    """Occlusion: the benchmark scene is one plane, so nothing there checks that the BVH returns the
+    NEAREST hit.  Here the plane lies behind a box and a soup of 300 random triangles that overlap each other along
+    the view rays, the model matrix is a general similarity, and a third of the primitives are masked out
+    (ray_casting.cc:71-105: masked primitives are skipped, not opaque).  Against the brute-force oracle
+    (oracle/raycast.py, every triangle tested): same hit flags, same primitive, and the hit distance is the minimum
+    over all unmasked triangles."""
+    w, h = 320, 240
+    clip = synth.Clip(w, h, 4, seed=9)
+    rng = np.random.default_rng(5)
+    pv, pt = synth.plane_mesh(w, h, clip.s, quads=16)
+    ext = np.abs(pv[:, :2]).max(0)
+    # a box between the camera and the plane (the camera sits at z ~ -depth in object space and looks at +z ... or the
+    # mirror image, depending on the convention: put occluders on both sides so that either way some are in front)
+    def box(c, r):
+        v = np.array([[x, y, z] for z in (-1, 1) for y in (-1, 1) for x in (-1, 1)], F) * r + c
+        t = np.array([[0, 1, 3], [0, 3, 2], [4, 7, 5], [4, 6, 7], [0, 4, 5], [0, 5, 1], [2, 3, 7], [2, 7, 6],
+                      [0, 2, 6], [0, 6, 4], [1, 5, 7], [1, 7, 3]], np.uint32)
+        return v, t
+    parts_v, parts_t, base = [pv.astype(F)], [pt.astype(np.uint32)], len(pv)
+    for zc in (-0.8, 0.8):
+        bv, bt = box(np.array([0.1 * ext[0], -0.05 * ext[1], zc], F), np.array([0.25 * ext[0], 0.2 * ext[1], 0.15], F))
+        parts_v.append(bv); parts_t.append(bt + base); base += len(bv)
+        c = np.stack([rng.uniform(-ext[0], ext[0], 150), rng.uniform(-ext[1], ext[1], 150), rng.uniform(0.2, 1.6, 150) * np.sign(zc)], 1)
+        sv = (c[:, None, :] + rng.normal(0, 0.12 * ext[0], (150, 3, 3))).reshape(-1, 3).astype(F)
+        parts_v.append(sv); parts_t.append(np.arange(450, dtype=np.uint32).reshape(150, 3) + base); base += len(sv)
+    verts, tris = np.concatenate(parts_v), np.concatenate(parts_t)
+    mask = np.zeros(((len(tris) + 31) // 32 + 3) // 4 * 4, np.uint32)          # padded to 4 words (geometry.h:63-65)
+    for p in rng.choice(len(tris), len(tris) // 3, replace=False):
+        mask[p // 32] |= np.uint32(1) << np.uint32(p % 32)
+    ang = 0.3
+    model = np.eye(4, dtype=F)
+    model[:3, :3] = 1.1 * np.array([[np.cos(ang), -np.sin(ang), 0], [np.sin(ang), np.cos(ang), 0], [0, 0, 1]], F)
+    model[:3, 3] = [0.05, -0.03, 0.1]
+    pos = np.stack([rng.uniform(-10, w + 10, 6000), rng.uniform(-10, h + 10, 6000)], 1).astype(F)
+    for conv in CONVENTIONS:
+        cam = H.oracle_cam(clip, 1, conv)
+        ctx_small.mesh_set(verts, tris, mask)
+        hit, P, prim, uv, t = ctx_small.ray_cast(model, H.to_abi(cam), pos, True)
+        o, d = oray.ray_object_space(model, cam.pose.Rt4x4(), cam.intrinsics, pos)
+        eh, eP, eprim, euv, et = oray.ray_cast(verts, tris, mask, o, d, True)
+        assert 0.3 < eh.mean()                                       # the camera sees the scene in this convention
+        front = eprim[eh] >= len(pt)                                 # hits on the occluders, not on the plane behind them
+        assert front.mean() > 0.2, front.mean()
+        assert (hit == eh).mean() > 0.998
+        both = hit & eh
+        assert (prim[both] == eprim[both]).mean() > 0.995
+        assert not np.any(mask[prim[both] // 32] >> (prim[both] % 32).astype(np.uint32) & 1)   # never a masked primitive
+        # nearest: wherever the primitive differs (grazing rays), the distance still is the minimum to 1e-4
+        assert np.percentile(np.abs(t[both] - et[both]) / np.maximum(np.abs(et[both]), 1e-6), 99.8) < 1e-4
+        hit2, P2, prim2, uv2, t2 = ctx_small.ray_cast(model, H.to_abi(cam), pos, False)     # masks ignored
+        eh2, _, eprim2, _, et2 = oray.ray_cast(verts, tris, mask, o, d, False)
+        assert (hit2 == eh2).mean() > 0.998 and (prim2[hit2 & eh2] == eprim2[hit2 & eh2]).mean() > 0.995
+        assert (et2[eh2 & eh] <= et[eh2 & eh] * (1 + 1e-6)).all()    # unmasking can only bring the hit nearer
+    ctx_small.mesh_set(verts[:3], np.array([[0, 1, 2]], np.uint32))
