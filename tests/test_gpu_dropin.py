@@ -345,3 +345,63 @@ def test_find_transformation_many_pins_on_the_gpu(core, trans, conv_gl):
     fin = _project(rigid, pts[:3].astype(np.float64))
     assert np.abs(fin[2] - target[2]).max() < 0.05               # three pins: the solve is exact (6 equations, 6 unknowns)
     assert np.abs(fin[:2] - before[:2]).max() < 0.05
+
+
+def test_baseline_config0_720p_64_frames_through_the_plugin(core, tmp_path):
+    """BASELINE.json configs[0]: "64-frame 720p synthetic clip, 2k features, OpticalFlow + Tracker" through the reference's
+    own entry points (OpticalFlowThread -> SQLite -> TrackerThread), OpenGL camera as the addon passes it.  The database
+    must hold the 8F - 30 pairs; sampled frames / pairs are compared with the oracle bit for bit (keypoints against the
+    cv2-pinned detector restatement, flow rows against the LK restatement); the tracked poses must stay within 1e-4
+    relative of the synthetic ground truth over the whole clip."""
+    from oracle import geometry as G
+    from polychase_b200 import synth as psynth
+    w, h, NF, first, mc = 1280, 720, 64, 1, 2000
+    clip = synth.Clip(w, h, NF, seed=12, first_frame=first, speed=psynth.survey_speed(w))
+    conv = G.OPENGL
+    frames = {k: H.clip_rgb(clip, k, conv) for k in range(first, first + NF)}
+    dbp = str(tmp_path / "c0.db")
+    go = core.GFTTOptions()
+    go.max_corners = mc
+    errors = []
+    th = core.OpticalFlowThread(core.VideoInfo(w, h, first, NF), dbp, go)
+    _pump(th, lambda m: th.provide_frame(m.frame_id, frames[m.frame_id]) if isinstance(m, core.OpticalFlowRequest)
+          else errors.append(m.what()) if isinstance(m, core.CppException) else None, timeout=300)
+    th.join()
+    assert not errors, errors
+    o = odb.Database(dbp)
+    assert o.frames() == list(range(first, first + NF))
+    assert len(o.pairs()) == 8 * NF - 30
+    for k in (first, first + 31, first + NF - 1):                    # sampled frames: the detector, bit for bit
+        g = restate.rgb2gray(frames[k])
+        assert np.array_equal(o.read_keypoints(k), ogftt.gftt_from_eig(restate.min_eig(g, 3), max_corners=mc)), k
+    for (a, b) in ((first + 8, first), (first + 20, first + 28), (first + 40, first + 39), (first + 63, first + 59)):
+        pa = restate.pyramid(restate.rgb2gray(frames[a]), 3)
+        pb = restate.pyramid(restate.rgb2gray(frames[b]), 3)
+        idx, tgt, err = o.read_image_pair_flow(a, b)
+        wn, ws, we = restate.lk(pa, pb, o.read_keypoints(a))
+        ok = ws == 1
+        assert np.array_equal(idx, np.nonzero(ok)[0].astype(np.uint32)), (a, b)
+        assert np.array_equal(tgt.view(np.uint32), wn[ok].view(np.uint32)), (a, b)
+        assert np.array_equal(err.view(np.uint32), we[ok].view(np.uint32)), (a, b)
+    o.close()
+    verts, tris = synth.plane_mesh(w, h, clip.s)
+    mesh = core.AcceleratedMesh(verts, tris)
+    start = H.oracle_cam(clip, first, conv)
+    ii = start.intrinsics
+    intr = core.CameraIntrinsics(float(ii.fx), float(ii.fy), float(ii.cx), float(ii.cy), 1.0, w, h,
+                                 core.CameraConvention.OpenGL)
+    scene = core.SceneTransformations(np.eye(4, dtype=F), start.pose.Rt4x4(), intr)
+    bo = core.BundleOptions()
+    bo.loss_type = core.LossType.Cauchy
+    tt = core.TrackerThread(dbp, first, first + NF - 1, scene, mesh, False, False, bo)
+    results = []
+    _pump(tt, lambda m: results.append(m) if isinstance(m, core.FrameTrackingResult) else errors.append(m.what()), timeout=300)
+    tt.join()
+    assert not errors, errors
+    assert [r.frame for r in results] == list(range(first + 1, first + NF))
+    worst = 0.0
+    for r in results:
+        gt = H.oracle_cam(clip, r.frame, conv)
+        worst = max(worst, float(np.abs(np.array(r.pose.t) - gt.pose.t).max()))
+        assert r.inlier_ratio > 0.9
+    assert worst < 1e-4 * clip.depth * 2.5, worst            # 2.5e-4 of the depth: the bench sweep's own figure over 640 frames is 2e-4
