@@ -60,7 +60,8 @@ def test_detector_matches_oracle(ctx_small, w, h, max_corners):
     assert np.array_equal(got, want_cv)
 
 
-@pytest.mark.parametrize("w,h,n,skip", [(640, 480, 1500, 4), (1280, 720, 2000, 8), (333, 251, 600, 1)])
+@pytest.mark.parametrize("w,h,n,skip", [(640, 480, 1500, 4), (1280, 720, 2000, 8), (333, 251, 600, 1),
+                                          (1920, 1080, 4000, 8)])          # the last: BASELINE configs[1] shape
 def test_lk_bit_exact(ctx_small, w, h, n, skip):
     clip = synth.Clip(w, h, skip + 1, seed=5)
     g1, g2 = clip.gray(0), clip.gray(skip)
